@@ -1,0 +1,47 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE (oracle) -- not part of the shipped product.
+#
+# Builds oracle/_ref/mrt_ref: the reference renderer itself (sources read from
+# $MRT_REFERENCE_DIR, default /root/reference; patched in a scratch directory by
+# patch_reference.py; nothing of the reference is copied into the repository)
+# plus ref_harness.cpp / ref_platform_headless.cpp from this directory.
+# Also stages the reference's data assets (earthmap.jpg, obj/*.obj) into the
+# git-ignored assets/ directory so that they travel to the GPU box, and decodes
+# earthmap.jpg once with the reference's vendored stb_image into assets/earthmap.ppm
+# (JPEG decoding is out of scope for the new host).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(dirname "$HERE")"
+SRC="${MRT_REFERENCE_DIR:-/root/reference}"
+OUT="$HERE/_ref"
+ASSETS="$ROOT/assets"
+if [ ! -d "$SRC" ]; then
+    echo "build_ref.sh: $SRC not present; keeping prebuilt $OUT/mrt_ref" >&2
+    [ -x "$OUT/mrt_ref" ] && exit 0 || exit 1
+fi
+mkdir -p "$OUT" "$ASSETS/obj" "$ASSETS/run"
+TMP="$(mktemp -d /tmp/mrt_ref_build.XXXXXX)"
+trap 'rm -rf "$TMP"' EXIT
+python3 "$HERE/patch_reference.py" "$SRC" "$TMP"
+cp "$HERE/ref_harness.cpp" "$HERE/ref_platform_headless.cpp" "$TMP/"
+FILES=""
+for f in "$TMP"/*.cpp; do
+    case "$(basename "$f")" in
+        main.cpp) ;;                      # included by ref_harness.cpp
+        *) FILES="$FILES $f" ;;
+    esac
+done
+# -march=x86-64-v3: AVX2 class (mat4.h uses AVX-256); portable to the GPU box's host CPU.
+# -ffp-contract=off: no FMA contraction, so results do not depend on the optimiser.
+g++ -std=c++20 -O3 -march=x86-64-v3 -ffp-contract=off -fno-exceptions -fpermissive \
+    -D__cdecl= -D__stdcall= -w -I"$SRC/include" -I"$TMP" $FILES -o "$OUT/mrt_ref" -lpthread
+# assets (data, not source)
+cp -f "$SRC/earthmap.jpg" "$ASSETS/earthmap.jpg"
+for o in bunny.obj Teapot3_no_vt.obj teapot.obj simple.obj pyramid.obj cylinder.obj; do
+    cp -f "$SRC/obj/$o" "$ASSETS/obj/$o"
+done
+# scene.cpp:509 asks for "teapot3_no_vt.obj"; the file is "Teapot3_no_vt.obj"
+cp -f "$SRC/obj/Teapot3_no_vt.obj" "$ASSETS/obj/teapot3_no_vt.obj"
+chmod -R u+w "$ASSETS"
+(cd "$ASSETS/run" && "$OUT/mrt_ref" dump-image ../earthmap.ppm)
+echo "built $OUT/mrt_ref"
