@@ -1,0 +1,276 @@
+// Flattener: host scene graph -> the typed structure-of-arrays tables of
+// mrt_types.h.  Topology, child order and the node_order bytes are preserved
+// exactly (the reference's traversal result depends on them).
+#include <cstring>
+#include <map>
+
+#include "scene_graph.h"
+
+namespace mrt {
+
+namespace {
+inline float ubits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline MrtF4 f4(float x, float y, float z, float w) { MrtF4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+struct Flattener {
+    const SceneGraph &g;
+    FlatScene &o;
+    std::map<int, uint32_t> memo;        // graph node -> typed ref
+    std::map<int, uint32_t> mat_memo;    // graph material -> flat material index
+    std::map<int, uint32_t> tex_memo;
+    std::vector<uint64_t> image_offset;
+    bool ok = true;
+
+    Flattener(const SceneGraph &g_, FlatScene &o_) : g(g_), o(o_) {}
+
+    void fail(const std::string &msg) { if (ok) o.error = msg; ok = false; }
+
+    bool tex_needs_uv(int t) const {
+        const Texture &x = g.texs[t];
+        if (x.kind == TexKind::Image) return true;
+        if (x.kind == TexKind::Checker) return tex_needs_uv(x.even) || tex_needs_uv(x.odd);
+        return false;
+    }
+    uint32_t tex(int t) {
+        auto it = tex_memo.find(t);
+        if (it != tex_memo.end()) return it->second;
+        const Texture &x = g.texs[t];
+        uint32_t even = 0, odd = 0;
+        if (x.kind == TexKind::Checker) { even = tex(x.even); odd = tex(x.odd); }
+        uint32_t id = (uint32_t) o.tex.size();
+        switch (x.kind) {
+        case TexKind::Color: o.tex.push_back(f4(ubits(MRT_X_COLOR), x.color.x, x.color.y, x.color.z)); break;
+        case TexKind::Checker: o.tex.push_back(f4(ubits(MRT_X_CHECKER), ubits(even), ubits(odd), x.scale)); break;
+        case TexKind::Perlin: o.tex.push_back(f4(ubits(MRT_X_PERLIN), x.scale, 0, 0)); break;
+        case TexKind::Image: {
+            const Image &im = g.images[x.image];
+            if (image_offset[x.image] > 0xFFFFFFFFull) fail("image table larger than 4 GiB");
+            o.tex.push_back(f4(ubits(MRT_X_IMAGE), ubits((uint32_t) im.width), ubits((uint32_t) im.height), ubits((uint32_t) image_offset[x.image])));
+            break;
+        }
+        }
+        tex_memo[t] = id;
+        return id;
+    }
+    uint32_t mat(int m) {
+        auto it = mat_memo.find(m);
+        if (it != mat_memo.end()) return it->second;
+        const Material &x = g.mats[m];
+        uint32_t kind = 0, t = 0;
+        bool uv = false;
+        switch (x.kind) {
+        case MatKind::Lambertian: kind = MRT_M_LAMBERTIAN; break;
+        case MatKind::Isotropic: kind = MRT_M_ISOTROPIC; break;
+        case MatKind::Metal: kind = MRT_M_METAL; break;
+        case MatKind::Dielectric: kind = MRT_M_DIELECTRIC; break;
+        case MatKind::Light: kind = MRT_M_LIGHT; break;
+        }
+        if (x.tex >= 0) { t = tex(x.tex); uv = tex_needs_uv(x.tex); }
+        uint32_t id = (uint32_t) o.mat.size();
+        o.mat.push_back(f4(ubits(kind | (uv ? MRT_MAT_NEEDS_UV : 0u)), ubits(t), x.param, 0));
+        mat_memo[m] = id;
+        return id;
+    }
+
+    bool contains_volume(int id) const {
+        const Node &n = g.nodes[id];
+        switch (n.kind) {
+        case NodeKind::Volume: return true;
+        case NodeKind::List: for (int c : n.children) if (contains_volume(c)) return true; return false;
+        case NodeKind::Bvh: return contains_volume(n.left) || contains_volume(n.right);
+        case NodeKind::Box: case NodeKind::Translate: case NodeKind::RotateY: return contains_volume(n.child);
+        default: return false;
+        }
+    }
+
+    uint32_t node(int id) {
+        auto it = memo.find(id);
+        if (it != memo.end()) return it->second;
+        const Node &n = g.nodes[id];
+        uint32_t ref = MRT_REF_NONE;
+        switch (n.kind) {
+        case NodeKind::Sphere: {
+            uint32_t i = (uint32_t) o.sphere.size() / 3;
+            uint32_t m = mat(n.mat);
+            o.sphere.push_back(f4(n.c0.x, n.c0.y, n.c0.z, n.radius));
+            o.sphere.push_back(f4(n.c1.x, n.c1.y, n.c1.z, ubits(m | (n.moving ? 0x80000000u : 0u))));
+            o.sphere.push_back(f4(n.t0, n.t1, 0, 0));
+            ref = MRT_REF(MRT_T_SPHERE, i);
+            break;
+        }
+        case NodeKind::RectXY:
+        case NodeKind::RectXZ:
+        case NodeKind::RectYZ: {
+            uint32_t i = (uint32_t) o.rect.size() / 2;
+            uint32_t m = mat(n.mat);
+            o.rect.push_back(f4(n.a0, n.a1, n.b0, n.b1));
+            o.rect.push_back(f4(n.k, n.sign, ubits(m), 0));
+            uint32_t type = n.kind == NodeKind::RectXY ? MRT_T_RECT_XY : (n.kind == NodeKind::RectXZ ? MRT_T_RECT_XZ : MRT_T_RECT_YZ);
+            ref = MRT_REF(type, i);
+            break;
+        }
+        case NodeKind::Box:   // box::hit forwards to its rect list (box.h:23-25)
+            ref = node(n.child);
+            break;
+        case NodeKind::List: {
+            std::vector<uint32_t> refs;
+            for (int c : n.children) refs.push_back(node(c));
+            uint32_t i = (uint32_t) o.list.size() / 2;
+            uint32_t first = (uint32_t) o.child.size();
+            for (uint32_t r : refs) o.child.push_back(r);
+            o.child.push_back(MRT_REF_END);
+            if (n.children.size() > 0x7FFFFFFFu) fail("list too long");
+            H3 mn = n.has_box ? n.box.min : H3(0, 0, 0), mx = n.has_box ? n.box.max : H3(0, 0, 0);
+            o.list.push_back(f4(mn.x, mn.y, mn.z, ubits(first)));
+            o.list.push_back(f4(mx.x, mx.y, mx.z, ubits((uint32_t) n.children.size() | (n.has_box ? 0x80000000u : 0u))));
+            ref = MRT_REF(MRT_T_LIST, i);
+            break;
+        }
+        case NodeKind::Bvh: {
+            uint32_t l = node(n.left), r = node(n.right);
+            uint32_t i = (uint32_t) o.bvh.size() / 2;
+            o.bvh.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(l | ((uint32_t) (n.order & 15u) << 28))));
+            o.bvh.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, ubits(r | ((uint32_t) (n.order >> 4) << 28))));
+            ref = MRT_REF(MRT_T_BVH, i);
+            break;
+        }
+        case NodeKind::Translate: {
+            uint32_t c = node(n.child);
+            uint32_t i = (uint32_t) o.xlate.size();
+            o.xlate.push_back(f4(n.offset.x, n.offset.y, n.offset.z, ubits(c)));
+            ref = MRT_REF(MRT_T_TRANSLATE, i);
+            break;
+        }
+        case NodeKind::RotateY: {
+            uint32_t c = node(n.child);
+            uint32_t i = (uint32_t) o.rot.size() / 3;
+            o.rot.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(c)));
+            o.rot.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, ubits(n.has_box ? 1u : 0u)));
+            o.rot.push_back(f4(n.sin_theta, n.cos_theta, 0, 0));
+            ref = MRT_REF(MRT_T_ROTATE_Y, i);
+            break;
+        }
+        case NodeKind::Volume: {
+            if (contains_volume(n.child)) fail("a constant_volume boundary must not contain another constant_volume");
+            uint32_t b = node(n.child);
+            uint32_t m = mat(n.mat);
+            uint32_t i = (uint32_t) o.vol.size();
+            o.vol.push_back(f4(ubits(b), n.density, ubits(m), 0));
+            ref = MRT_REF(MRT_T_VOLUME, i);
+            break;
+        }
+        case NodeKind::PodBvh: {
+            const Mesh &mesh = g.meshes[n.mesh];
+            uint32_t m = mat(mesh.mat);
+            uint32_t node_base = (uint32_t) o.pod.size() / 2;
+            uint32_t tri_base = (uint32_t) o.tri.size() / 3;
+            for (const PodNode &pn : mesh.nodes) {
+                if (pn.prim_count > 0xFFFFu) fail("pod_bvh leaf with more than 65535 triangles");
+                uint32_t w0 = pn.prim_count ? tri_base + pn.prim_offset : node_base + pn.left;
+                uint32_t w1 = pn.prim_count ? pn.prim_count : ((uint32_t) pn.order << 16);
+                o.pod.push_back(f4(pn.box.min.x, pn.box.min.y, pn.box.min.z, ubits(w0)));
+                o.pod.push_back(f4(pn.box.max.x, pn.box.max.y, pn.box.max.z, ubits(w1)));
+            }
+            for (const Triangle &t : mesh.tris) {
+                o.tri.push_back(f4(t.m.x, t.m.y, t.m.z, ubits(m)));
+                o.tri.push_back(f4(t.u.x, t.u.y, t.u.z, 0));
+                o.tri.push_back(f4(t.v.x, t.v.y, t.v.z, 0));
+                o.trin.push_back(f4(t.mn.x, t.mn.y, t.mn.z, 0));
+                o.trin.push_back(f4(t.un.x, t.un.y, t.un.z, 0));
+                o.trin.push_back(f4(t.vn.x, t.vn.y, t.vn.z, 0));
+            }
+            ref = MRT_REF(MRT_T_POD, node_base);
+            break;
+        }
+        }
+        memo[id] = ref;
+        return ref;
+    }
+
+    // worst-case number of 32-bit stack words `intersect` needs below this node (trace_core.h)
+    uint32_t pod_depth(const Mesh &m, uint32_t ni) const {
+        const PodNode &pn = m.nodes[ni];
+        if (pn.prim_count) return 0;
+        return 1 + std::max(pod_depth(m, pn.left), pod_depth(m, pn.left + 1));
+    }
+    uint32_t depth(int id) const {
+        const Node &n = g.nodes[id];
+        switch (n.kind) {
+        case NodeKind::List: {
+            uint32_t d = 0;
+            for (int c : n.children) d = std::max(d, depth(c));
+            return 1 + d;
+        }
+        case NodeKind::Box: return depth(n.child);
+        case NodeKind::Bvh: return 1 + std::max(depth(n.left), depth(n.right));
+        case NodeKind::Translate:
+        case NodeKind::RotateY: return 11 + depth(n.child);
+        case NodeKind::Volume: return 1 + depth(n.child);
+        case NodeKind::PodBvh: return pod_depth(g.meshes[n.mesh], 0);
+        default: return 0;
+        }
+    }
+};
+}  // namespace
+
+bool flatten_scene(const SceneGraph &g, FlatScene *out) {
+    FlatScene &o = *out;
+    o = FlatScene();
+    Flattener fl(g, o);
+    uint64_t off = 0;
+    for (const Image &im : g.images) {
+        fl.image_offset.push_back(off);
+        o.image.insert(o.image.end(), im.rgb.begin(), im.rgb.end());
+        off += im.rgb.size();
+    }
+    uint32_t root = fl.node(g.objects);
+    if (g.biased >= 0) {
+        const Node &b = g.nodes[g.biased];
+        if (b.kind != NodeKind::List) fl.fail("biased_objects must be an object_list");
+        else for (int c : b.children) o.lights.push_back(fl.node(c));
+    }
+    if (g.uses_perlin) {
+        const PerlinTables &pt = perlin_tables();
+        for (int i = 0; i < 256; i++) o.perlin_vec.push_back(f4(pt.ranvec[i][0], pt.ranvec[i][1], pt.ranvec[i][2], 0));
+        for (int a = 0; a < 3; a++) for (int i = 0; i < 256; i++) o.perlin_perm.push_back(pt.perm[a][i]);
+    }
+    const size_t lim = 0xFFFFFFu;
+    if (o.sphere.size() / 3 > lim || o.rect.size() / 2 > lim || o.list.size() / 2 > lim || o.bvh.size() / 2 > lim ||
+        o.pod.size() / 2 > lim || o.xlate.size() > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
+        fl.fail("too many objects of one type for a 24-bit index");
+    if (o.child.size() > 0x0FFFFFFFu) fl.fail("child table too large");
+    if (!fl.ok) return false;
+
+    MrtSceneDesc &d = o.desc;
+    memset(&d, 0, sizeof(d));
+    d.root = root;
+    d.n_lights = (uint32_t) o.lights.size();
+    d.lights = o.lights.data();
+    d.sky = g.sky ? 1u : 0u;
+    d.stack_words = fl.depth(g.objects) + 2;
+    const Camera &c = g.camera;
+    auto put = [](float *dst, H3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; };
+    put(d.camera.origin, c.origin); put(d.camera.u, c.u); put(d.camera.v, c.v); put(d.camera.w, c.w);
+    put(d.camera.llcorner, c.llcorner); put(d.camera.horz, c.horz); put(d.camera.vert, c.vert);
+    d.camera.lens_radius = c.lens_radius; d.camera.time0 = c.time0; d.camera.time1 = c.time1;
+    d.sphere = o.sphere.data(); d.n_sphere = (uint32_t) o.sphere.size() / 3;
+    d.rect = o.rect.data();     d.n_rect = (uint32_t) o.rect.size() / 2;
+    d.list = o.list.data();     d.n_list = (uint32_t) o.list.size() / 2;
+    d.child = o.child.data();   d.n_child = (uint32_t) o.child.size();
+    d.bvh = o.bvh.data();       d.n_bvh = (uint32_t) o.bvh.size() / 2;
+    d.pod = o.pod.data();       d.n_pod = (uint32_t) o.pod.size() / 2;
+    d.tri = o.tri.data();       d.n_tri = (uint32_t) o.tri.size() / 3;
+    d.trin = o.trin.data();
+    d.xlate = o.xlate.data();   d.n_xlate = (uint32_t) o.xlate.size();
+    d.rot = o.rot.data();       d.n_rot = (uint32_t) o.rot.size() / 3;
+    d.vol = o.vol.data();       d.n_vol = (uint32_t) o.vol.size();
+    d.mat = o.mat.data();       d.n_mat = (uint32_t) o.mat.size();
+    d.tex = o.tex.data();       d.n_tex = (uint32_t) o.tex.size();
+    d.perlin_vec = o.perlin_vec.empty() ? nullptr : o.perlin_vec.data();
+    d.perlin_perm = o.perlin_perm.empty() ? nullptr : o.perlin_perm.data();
+    d.image = o.image.empty() ? nullptr : o.image.data();
+    d.n_image_bytes = o.image.size();
+    return true;
+}
+
+}  // namespace mrt

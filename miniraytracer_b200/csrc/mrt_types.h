@@ -1,0 +1,137 @@
+// Flattened GPU scene layout shared by the host flattener, the CUDA kernels and
+// the C ABI (include/mrt_gpu.h re-exports the POD description).
+//
+// The reference scene is a pointer graph of virtual scene_object's
+// (scene_object.h:20-31).  Here every object lives in a typed structure-of-
+// arrays table of 16-byte records (read with one coalesced/vectorised 128-bit
+// load each) and is addressed by a 28-bit typed reference:
+//
+//      ref = (type << 24) | index          type: 4 bits, index: 24 bits
+//
+// Tables (all `MrtF4`, 16 B aligned):
+//   sphere[3*i+0] = (c0.x, c0.y, c0.z, radius)                 sphere.h:11-17
+//   sphere[3*i+1] = (c1.x, c1.y, c1.z, bits(mat | moving<<31))
+//   sphere[3*i+2] = (time0, time1, 0, 0)
+//   rect[2*i+0]   = (a0, a1, b0, b1)                            rect.h:6-11
+//   rect[2*i+1]   = (k, normal_sign, bits(mat), 0)     axis is in the ref type
+//   list[2*i+0]   = (box.min.xyz, bits(first_child))            scene_object.h:37-44
+//   list[2*i+1]   = (box.max.xyz, bits(count | hasBox<<31))
+//                   children = child[first_child .. +count], then MRT_REF_END
+//   bvh[2*i+0]    = (box.min.xyz, bits(left  | (order & 15) << 28))   scene_object.h:138-144
+//   bvh[2*i+1]    = (box.max.xyz, bits(right | (order >> 4) << 28))
+//   pod[2*i+0]    = (box.min.xyz, bits(left or first triangle))       triangle.h:46-56
+//   pod[2*i+1]    = (box.max.xyz, bits(prim_count | order << 16))  prim_count==0: inner
+//                   (left / first triangle are absolute indices into pod[] / tri[])
+//   tri[3*i+0..2] = (m.xyz, bits(mat)), (u.xyz, 0), (v.xyz, 0)         triangle.h:13-22
+//   trin[3*i+0..2]= (mn.xyz,0), (un.xyz,0), (vn.xyz,0)
+//   xlate[i]      = (offset.xyz, bits(child))                          scene_object.h:325-333
+//   rot[3*i+0]    = (bbox.min.xyz, bits(child))                        scene_object.h:340-355
+//   rot[3*i+1]    = (bbox.max.xyz, bits(hasBox))
+//   rot[3*i+2]    = (sin_theta, cos_theta, 0, 0)
+//   vol[i]        = (bits(boundary), density, bits(mat), 0)            volumes.h:8-12
+//   mat[i]        = (bits(kind | needs_uv<<8), bits(tex), param, 0)    material.h
+//   tex[i]        = COLOR  (bits(kind), r, g, b)                       texture.h
+//                   CHECKER(bits(kind), bits(even), bits(odd), scale)
+//                   PERLIN (bits(kind), scale, 0, 0)
+//                   IMAGE  (bits(kind), bits(width), bits(height), bits(byte offset into image[]))
+//   perlin_vec[256] = (ranvec.xyz, 0)   perlin_perm[3*256] = perm_x,perm_y,perm_z (texture.cpp:107-112)
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+#if defined(__GNUC__) || defined(__CUDACC__)
+    __attribute__((aligned(16)))
+#endif
+    MrtF4 {
+    float x, y, z, w;
+} MrtF4;
+
+enum MrtRefType {
+    MRT_T_SPHERE = 0,
+    MRT_T_RECT_XY = 1,
+    MRT_T_RECT_XZ = 2,
+    MRT_T_RECT_YZ = 3,
+    MRT_T_LIST = 4,
+    MRT_T_BVH = 5,
+    MRT_T_POD = 6,
+    MRT_T_TRANSLATE = 7,
+    MRT_T_ROTATE_Y = 8,
+    MRT_T_VOLUME = 9,
+    MRT_T_END = 15 /* list terminator */
+};
+#define MRT_REF(type, index) ((uint32_t) (((uint32_t) (type) << 24) | ((uint32_t) (index) & 0xFFFFFFu)))
+#define MRT_REF_TYPE(ref) (((ref) >> 24) & 15u)
+#define MRT_REF_INDEX(ref) ((ref) & 0xFFFFFFu)
+#define MRT_REF_END MRT_REF(MRT_T_END, 0)
+#define MRT_REF_NONE 0xFFFFFFFFu
+
+enum MrtMatKind {
+    MRT_M_LAMBERTIAN = 0,
+    MRT_M_ISOTROPIC = 1,
+    MRT_M_METAL = 2,
+    MRT_M_DIELECTRIC = 3,
+    MRT_M_LIGHT = 4
+};
+#define MRT_MAT_NEEDS_UV 0x100u
+
+enum MrtTexKind { MRT_X_COLOR = 0, MRT_X_CHECKER = 1, MRT_X_PERLIN = 2, MRT_X_IMAGE = 3 };
+
+/* camera.h:8-14 */
+typedef struct MrtCamera {
+    float origin[3];
+    float u[3], v[3], w[3];
+    float llcorner[3];
+    float horz[3];
+    float vert[3];
+    float lens_radius;
+    float time0, time1;
+} MrtCamera;
+
+/* The flattened scene.  All pointers are HOST pointers when handed to
+   mrt_gpu_scene_upload(); the library owns its device copies. */
+typedef struct MrtSceneDesc {
+    uint32_t root;            /* typed ref of scene.objects (scene.h:20) */
+    uint32_t n_lights;        /* scene.biased_objects: object_list count (0 = nullptr) */
+    const uint32_t *lights;   /* typed refs (sphere or xz_rect have a pdf; others evaluate to 0) */
+    uint32_t sky;             /* 1: sky gradient on miss (sceneSelect < SCENE_CORNELL_BOX, main.cpp:110) */
+    uint32_t stack_words;     /* worst-case traversal stack depth in 32-bit words (computed by the flattener) */
+    MrtCamera camera;
+
+    const MrtF4 *sphere;  uint32_t n_sphere;
+    const MrtF4 *rect;    uint32_t n_rect;
+    const MrtF4 *list;    uint32_t n_list;
+    const uint32_t *child; uint32_t n_child;
+    const MrtF4 *bvh;     uint32_t n_bvh;
+    const MrtF4 *pod;     uint32_t n_pod;
+    const MrtF4 *tri;     uint32_t n_tri;
+    const MrtF4 *trin;
+    const MrtF4 *xlate;   uint32_t n_xlate;
+    const MrtF4 *rot;     uint32_t n_rot;
+    const MrtF4 *vol;     uint32_t n_vol;
+    const MrtF4 *mat;     uint32_t n_mat;
+    const MrtF4 *tex;     uint32_t n_tex;
+    const MrtF4 *perlin_vec;      /* 256 entries or NULL */
+    const int32_t *perlin_perm;   /* 768 entries or NULL */
+    const uint8_t *image;  uint64_t n_image_bytes;   /* all RGB8 images, concatenated */
+} MrtSceneDesc;
+
+/* One render call = all pixels x samples [sample_begin, sample_end). */
+typedef struct MrtRenderParams {
+    uint32_t width, height;
+    uint32_t samples;         /* N = floor(sqrt(spp))^2 (main.cpp:319-320); the stream id uses this N */
+    uint32_t sample_begin, sample_end;
+    uint32_t max_bounces;     /* MRT_Params::maxBounces (cmdline_parser.h:13) */
+    uint64_t seed;            /* PCG32 initstate; the stream (initseq) is (y*W+x)*N+s */
+    float max_luminance;      /* applied by finalize only (main.cpp:170-173) */
+    uint32_t flags;           /* MRT_RENDER_* */
+} MrtRenderParams;
+
+#define MRT_RENDER_ACCUMULATE 1u /* add to the accumulator instead of overwriting it */
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,897 @@
+// Per-path tracer core: camera ray generation, scene traversal, primitive hit
+// tests, material scatter, mixture-pdf light sampling, textures and the PCG32
+// generator -- the body of the reference's hot path (main.cpp:66-188 and
+// everything it calls), rebuilt as an iterative, stack-machine tracer over the
+// flattened scene of mrt_types.h.
+//
+// The functions are written once and compiled by nvcc for sm_100a (the product)
+// and, for logic tests only, by g++ (tests/host_emul) -- the shipped library
+// has no CPU execution path.
+//
+// Arithmetic contract (what "parity" means): every
+// floating-point expression keeps the reference's operation order, divisions
+// and square roots are IEEE (no rsqrt / reciprocal shortcuts), and the file is
+// compiled with -fmad=false (nvcc) / -ffp-contract=off (g++) so that no
+// multiply-add is fused.  Only libm calls (sinf cosf atan2f asinf logf powf)
+// may differ from the CPU by the library's ulp error.
+#pragma once
+#include "mrt_types.h"
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define MRT_HD __host__ __device__ __forceinline__
+#else
+#define MRT_HD inline
+#endif
+
+namespace mrt {
+
+#define MRT_PI_F 3.14159265358979323846f /* mrt_math.h:11 */
+
+// ------------------------------------------------------------------ utilities
+MRT_HD uint32_t f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+MRT_HD float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+MRT_HD float fsqrt(float x) {  // MRT::sqrt = sqrtss (mrt_math.h:76-78): correctly rounded
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(x);
+#else
+    return sqrtf(x);
+#endif
+}
+MRT_HD float fdiv(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+MRT_HD bool is_finite(float x) { return (f2u(x) & 0x7F800000u) != 0x7F800000u; }
+
+MRT_HD MrtF4 ld4(const MrtF4 *p, uint32_t i) {
+#ifdef __CUDA_ARCH__
+    float4 v = __ldg(reinterpret_cast<const float4 *>(p) + i);
+    MrtF4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    return p[i];
+#endif
+}
+MRT_HD uint32_t ldu(const uint32_t *p, uint32_t i) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p + i);
+#else
+    return p[i];
+#endif
+}
+
+struct V3 { float x, y, z; };
+MRT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+MRT_HD V3 v3(const MrtF4 &f) { return v3(f.x, f.y, f.z); }
+MRT_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MRT_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+MRT_HD V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+MRT_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+MRT_HD V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+MRT_HD V3 operator/(V3 a, float s) { return v3(fdiv(a.x, s), fdiv(a.y, s), fdiv(a.z, s)); }
+MRT_HD V3 neg(V3 a) { return v3(-a.x, -a.y, -a.z); }
+// vec3.h:245-248 : (x + y) + z
+MRT_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+MRT_HD float sdot(V3 a) { return dot(a, a); }
+// vec3.h:250-266
+MRT_HD V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// vec3.h:137-139 : v / sqrt(v.v)
+MRT_HD V3 normalize(V3 a) { return a / fsqrt(sdot(a)); }
+
+// ---------------------------------------------------------------------- PCG32
+// pcg.cpp:13-35,53-62
+struct Rng { uint64_t state, inc; };
+MRT_HD uint32_t rng_next(Rng &r) {
+    uint64_t old = r.state;
+    r.state = old * 6364136223846793005ULL + r.inc;
+    uint32_t xorshifted = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t) (old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+}
+MRT_HD void rng_seed(Rng &r, uint64_t initstate, uint64_t initseq) {
+    r.state = 0u;
+    r.inc = (initseq << 1u) | 1u;
+    rng_next(r);
+    r.state += initstate;
+    rng_next(r);
+}
+MRT_HD float randf(Rng &r) { return u2f(0x3f800000u | (rng_next(r) & 0x007FFFFFu)) - 1.0f; }
+// pcg.cpp:70-77 (draw order x, y, z)
+MRT_HD V3 random_in_sphere(Rng &r) {
+    V3 p;
+    do {
+        float rx = randf(r), ry = randf(r), rz = randf(r);
+        p = v3(2.0f * rx - 1.0f, 2.0f * ry - 1.0f, 2.0f * rz - 1.0f);
+    } while (sdot(p) >= 1.0f);
+    return p;
+}
+// pcg.cpp:112-119
+MRT_HD V3 random_in_disk(Rng &r) {
+    V3 p;
+    do {
+        float rx = randf(r), ry = randf(r);
+        p = v3(2.0f * rx - 1.0f, 2.0f * ry - 1.0f, 0.0f);
+    } while (sdot(p) >= 1.0f);
+    return p;
+}
+// pcg.cpp:87-95 (the factor 2 on x,y is the reference's)
+MRT_HD V3 random_cosine_direction(Rng &r) {
+    float r1 = randf(r);
+    float r2 = randf(r);
+    float z = fsqrt(1 - r2);
+    float phi = 2 * MRT_PI_F * r1;
+    float sr2 = fsqrt(r2);
+    float x = cosf(phi) * 2 * sr2;
+    float y = sinf(phi) * 2 * sr2;
+    return v3(x, y, z);
+}
+// pcg.cpp:125-133
+MRT_HD V3 random_towards_sphere(float radius, float dist_sq, Rng &r) {
+    float r1 = randf(r);
+    float r2 = randf(r);
+    float z = 1 + r2 * (fsqrt(1 - fdiv(radius * radius, dist_sq)) - 1);
+    float phi = 2 * MRT_PI_F * r1;
+    float s = fsqrt(1 - z * z);
+    float x = cosf(phi) * s;
+    float y = sinf(phi) * s;
+    return v3(x, y, z);
+}
+
+// ------------------------------------------------------------------------ ray
+// ray.h:7-52.  inv = 1/dir is what aabb::hit recomputes per test (aabb.h:49).
+struct Ray {
+    V3 o, d, inv;
+    float time;
+    int inside;
+    uint32_t mask;
+};
+MRT_HD uint32_t dir_mask(V3 d) {
+    uint32_t X = f2u(d.x) >> 31, Y = f2u(d.y) >> 31, Z = f2u(d.z) >> 31;
+    return 1u << (Z | (Y << 1) | (X << 2));
+}
+MRT_HD void ray_set_dir(Ray &r, V3 dir) {  // direction is normalised by the ctor (ray.h:30)
+    r.d = normalize(dir);
+    r.inv = v3(fdiv(1.0f, r.d.x), fdiv(1.0f, r.d.y), fdiv(1.0f, r.d.z));
+    r.mask = dir_mask(r.d);
+}
+MRT_HD Ray make_ray(V3 o, V3 dir, float time, int inside) {
+    Ray r;
+    r.o = o;
+    r.time = time;
+    r.inside = inside;
+    ray_set_dir(r, dir);
+    return r;
+}
+MRT_HD V3 ray_eval(const Ray &r, float t) { return r.o + t * r.d; }
+
+// aabb.h:45-76 with the SSE min/max NaN rule (second operand wins) and strict >
+MRT_HD bool aabb_hit(const MrtF4 &bmin, const MrtF4 &bmax, const Ray &r, float tmin, float tmax) {
+    float t0x = (bmin.x - r.o.x) * r.inv.x, t1x = (bmax.x - r.o.x) * r.inv.x;
+    float t0y = (bmin.y - r.o.y) * r.inv.y, t1y = (bmax.y - r.o.y) * r.inv.y;
+    float t0z = (bmin.z - r.o.z) * r.inv.z, t1z = (bmax.z - r.o.z) * r.inv.z;
+    if (r.inv.x < 0.0f) { float t = t0x; t0x = t1x; t1x = t; }
+    if (r.inv.y < 0.0f) { float t = t0y; t0y = t1y; t1y = t; }
+    if (r.inv.z < 0.0f) { float t = t0z; t0z = t1z; t1z = t; }
+    float a0 = (t0x > t0z) ? t0x : t0z;
+    float a1 = (t0y > tmin) ? t0y : tmin;
+    float lo = (a0 > a1) ? a0 : a1;
+    float b0 = (t1x < t1z) ? t1x : t1z;
+    float b1 = (t1y < tmax) ? t1y : tmax;
+    float hi = (b0 < b1) ? b0 : b1;
+    return hi > lo;
+}
+
+// -------------------------------------------------------------- scene (device)
+struct SceneView {
+    const MrtF4 *sphere, *rect, *list, *bvh, *pod, *tri, *trin, *xlate, *rot, *vol, *mat, *tex, *perlin_vec;
+    const uint32_t *child, *lights;
+    const int32_t *perlin_perm;
+    const uint8_t *image;
+    uint32_t root, n_lights, sky;
+    MrtCamera cam;
+};
+
+struct Hit {   // hit_record, scene_object.h:10-17
+    float t;
+    V3 p, n;
+    float u, v;
+    uint32_t mat;
+};
+
+// Traversal stack: 32-bit words, one column per thread.  On the GPU the columns
+// of a warp are interleaved in shared memory (word k of lane l at base[k*32+l])
+// so that every push/pop is conflict free.
+struct Stack {
+    uint32_t *base;
+    uint32_t stride;
+    uint32_t sp;
+    MRT_HD void push(uint32_t v) { base[sp * stride] = v; sp++; }
+    MRT_HD uint32_t pop() { sp--; return base[sp * stride]; }
+    MRT_HD void pushf(float f) { push(f2u(f)); }
+    MRT_HD float popf() { return u2f(pop()); }
+};
+
+// frame tags (top 3 bits of a stack word); payload = low 28 bits, bit 28 = list "found" flag
+#define MRT_F_IF_MISS 1u   /* bvh: visit payload ref only if the closer child missed */
+#define MRT_F_LIST 2u      /* object_list continuation: payload = index into child[] */
+#define MRT_F_XLATE_END 3u /* translate: restore ray, rec.p += offset */
+#define MRT_F_ROT_END 4u   /* rotate_y: restore ray, rotate rec.p / rec.n back */
+#define MRT_F_VOL1 5u      /* constant_volume: first boundary hit returned */
+#define MRT_F_VOL2 6u      /* constant_volume: second boundary hit returned */
+#define MRT_FRAME(tag, payload) (((tag) << 29) | (payload))
+
+struct Counters {   // optional algorithmic op counters
+    unsigned long long rays, aabb, sphere, rect, tri, vol, xform;
+};
+
+// ----------------------------------------------------------- primitive tests
+MRT_HD V3 sphere_center(const MrtF4 &s0, const MrtF4 &s1, const MrtF4 *tab, uint32_t idx, float time) {
+    if (f2u(s1.w) >> 31) {  // isMoving, sphere.h:24-31
+        MrtF4 s2 = ld4(tab, 3 * idx + 2);
+        float k = fdiv(time - s2.x, s2.y - s2.x);
+        return v3(s0) + k * (v3(s1) - v3(s0));
+    }
+    return v3(s0);
+}
+MRT_HD void sphere_uv(V3 n, float *u, float *v) {  // sphere.cpp:6-11
+    float phi = atan2f(n.z, n.x);
+    float theta = asinf(n.y);
+    *u = 0.5f - phi * (1.0f / (2.0f * MRT_PI_F));
+    *v = 0.5f + theta * (1.0f / MRT_PI_F);
+}
+// sphere.cpp:13-46.  full=false: only the distance is wanted (volume boundary probe).
+MRT_HD bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+    MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
+    V3 cen = sphere_center(s0, s1, sc.sphere, idx, r.time);
+    float radius = s0.w;
+    V3 oc = r.o - cen;
+    float b = dot(oc, r.d);
+    float c = sdot(oc) - radius * radius;
+    float disc = b * b - c;
+    if (disc > 0) {
+        float sq = fsqrt(disc);
+        float t = (-b - sq);
+        bool ok = (t < tmax && t > tmin);
+        if (!ok && r.inside) {
+            t = (-b + sq);
+            ok = (t < tmax && t > tmin);
+        }
+        if (ok) {
+            rec.t = t;
+            if (full) {
+                uint32_t mat = f2u(s1.w) & 0x7FFFFFFFu;
+                rec.p = ray_eval(r, t);
+                rec.n = (rec.p - cen) / radius;
+                rec.mat = mat;
+                if (f2u(ld4(sc.mat, mat).x) & MRT_MAT_NEEDS_UV) sphere_uv(rec.n, &rec.u, &rec.v);
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// rect.cpp:24-45,69-90,130-152.  axis = 0: xy (k=z), 1: xz (k=y), 2: yz (k=x)
+MRT_HD bool hit_rect(const SceneView &sc, uint32_t axis, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+    MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
+    float ok_, dk, oa, da, ob, db;
+    if (axis == 0)      { ok_ = r.o.z; dk = r.d.z; oa = r.o.x; da = r.d.x; ob = r.o.y; db = r.d.y; }
+    else if (axis == 1) { ok_ = r.o.y; dk = r.d.y; oa = r.o.x; da = r.d.x; ob = r.o.z; db = r.d.z; }
+    else                { ok_ = r.o.x; dk = r.d.x; oa = r.o.y; da = r.d.y; ob = r.o.z; db = r.d.z; }
+    float ns = q1.y;
+    if (dk * ns > 0.0f) return false;   // one-sided
+    float t = fdiv(q1.x - ok_, dk);
+    if (t < tmin || t > tmax) return false;
+    float a = oa + t * da;
+    float b = ob + t * db;
+    if (a < q0.x || a > q0.y || b < q0.z || b > q0.w) return false;
+    rec.t = t;
+    if (full) {
+        rec.mat = f2u(q1.z);
+        if (f2u(ld4(sc.mat, rec.mat).x) & MRT_MAT_NEEDS_UV) {
+            rec.u = fdiv(a - q0.x, q0.y - q0.x);
+            rec.v = fdiv(b - q0.z, q0.w - q0.z);
+        }
+        rec.p = ray_eval(r, t);
+        rec.n = (axis == 0) ? v3(0, 0, ns) : (axis == 1) ? v3(0, ns, 0) : v3(ns, 0, 0);
+    }
+    return true;
+}
+
+// triangle.cpp:222-266 (Moeller-Trumbore path; NEW_INTERSECT is off, common.h:7)
+MRT_HD bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+    MrtF4 tm = ld4(sc.tri, 3 * idx), tu = ld4(sc.tri, 3 * idx + 1), tv = ld4(sc.tri, 3 * idx + 2);
+    V3 u = v3(tu), v = v3(tv);
+    V3 pvec = cross(r.d, v);
+    float det = dot(u, pvec);
+    float sign = 1.0f;
+    if (r.inside) {
+        sign = det < 0.0f ? -1.0f : 1.0f;
+        det = sign * det;
+    }
+    if (det < 0.00001f) return false;
+    V3 tvec = r.o - v3(tm);
+    float uu = dot(tvec, pvec) * sign;
+    V3 qvec = cross(tvec, u);
+    float vv = dot(r.d, qvec) * sign;
+    if ((uu < 0) | (uu > det) | (vv < 0) | ((uu + vv) > det)) return false;
+    float invDet = fdiv(1, det);
+    float t = dot(v, qvec) * invDet * sign;
+    if ((t < tmin) | (t > tmax)) return false;
+    rec.t = t;
+    if (full) {
+        uu *= invDet;
+        vv *= invDet;
+        V3 mn = v3(ld4(sc.trin, 3 * idx)), un = v3(ld4(sc.trin, 3 * idx + 1)), vn = v3(ld4(sc.trin, 3 * idx + 2));
+        rec.p = ray_eval(r, t);
+        rec.n = normalize(((mn * (1 - uu - vv)) + (un * uu)) + (vn * vv));
+        rec.u = uu;
+        rec.v = vv;
+        rec.mat = f2u(tm.w);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ traversal
+// scene.hit(r, tmin, tmax, &rec) of the reference, for any nesting of
+// object_list / bvh_node / pod_bvh / translate / rotate_y / constant_volume.
+// Invariants that make one hit record and one (tmin, tmax) pair sufficient:
+//  * object_list (scene_object.h:79-103) passes its shrinking `closest` down,
+//    so any hit reported by a nested container supersedes the list's best;
+//  * bvh_node / pod_bvh (scene_object.h:208-244, triangle.h:171-213) return on
+//    the first child (front-to-back by node_order & dirMask) that reports a
+//    hit and never tighten tmax between children -> IF_MISS frames;
+//  * constant_volume (volumes.cpp:5-36) probes its boundary twice with private
+//    (tmin, tmax) and only needs the two distances -> `probe` mode, in which
+//    hits update tmax only and the main record is untouched.  A volume's
+//    boundary must not contain another volume (checked by the flattener).
+MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
+                      Counters *cnt) {
+    float tmin = tmin0, tmax = tmax0;
+    float main_tmax = tmax0;
+    bool probe = false;
+    float vol_t1 = 0.0f;
+    uint32_t cur = sc.root;
+    bool ret = false;
+    const uint32_t sp0 = st.sp;
+
+    for (;;) {
+        // ------------------------------------------------------------ visit
+        bool descend = true;
+        while (descend) {
+            descend = false;
+            const uint32_t type = MRT_REF_TYPE(cur), idx = MRT_REF_INDEX(cur);
+            switch (type) {
+            case MRT_T_SPHERE:
+                if (cnt) cnt->sphere++;
+                ret = hit_sphere(sc, idx, ray, tmin, tmax, !probe, rec);
+                if (ret) tmax = rec.t;
+                break;
+            case MRT_T_RECT_XY:
+            case MRT_T_RECT_XZ:
+            case MRT_T_RECT_YZ:
+                if (cnt) cnt->rect++;
+                ret = hit_rect(sc, type - MRT_T_RECT_XY, idx, ray, tmin, tmax, !probe, rec);
+                if (ret) tmax = rec.t;
+                break;
+            case MRT_T_LIST: {
+                MrtF4 l0 = ld4(sc.list, 2 * idx), l1 = ld4(sc.list, 2 * idx + 1);
+                ret = false;
+                if (f2u(l1.w) >> 31) {
+                    if (cnt) cnt->aabb++;
+                    if (!aabb_hit(l0, l1, ray, tmin, tmax)) break;
+                }
+                st.push(MRT_FRAME(MRT_F_LIST, f2u(l0.w)));
+                break;   // the LIST frame is popped right away and runs the child loop
+            }
+            case MRT_T_BVH: {
+                MrtF4 b0 = ld4(sc.bvh, 2 * idx), b1 = ld4(sc.bvh, 2 * idx + 1);
+                if (cnt) cnt->aabb++;
+                ret = false;
+                if (!aabb_hit(b0, b1, ray, tmin, tmax)) break;
+                uint32_t w0 = f2u(b0.w), w1 = f2u(b1.w);
+                uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
+                uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
+                bool lfirst = (order & ray.mask) != 0;
+                st.push(MRT_FRAME(MRT_F_IF_MISS, lfirst ? right : left));
+                cur = lfirst ? left : right;
+                descend = true;
+                break;
+            }
+            case MRT_T_POD: {
+                MrtF4 p0 = ld4(sc.pod, 2 * idx), p1 = ld4(sc.pod, 2 * idx + 1);
+                if (cnt) cnt->aabb++;
+                ret = false;
+                if (!aabb_hit(p0, p1, ray, tmin, tmax)) break;
+                uint32_t w1 = f2u(p1.w);
+                uint32_t count = w1 & 0xFFFFu;
+                if (count) {   // leaf: closest hit among its triangles (triangle.h:179-187)
+                    uint32_t first = f2u(p0.w);
+                    for (uint32_t i = 0; i < count; i++) {
+                        if (cnt) cnt->tri++;
+                        if (hit_triangle(sc, first + i, ray, tmin, tmax, !probe, rec)) {
+                            ret = true;
+                            tmax = rec.t;
+                        }
+                    }
+                } else {
+                    uint32_t order = (w1 >> 16) & 0xFFu;
+                    uint32_t left = f2u(p0.w);
+                    bool lfirst = (order & ray.mask) != 0;
+                    st.push(MRT_FRAME(MRT_F_IF_MISS, MRT_REF(MRT_T_POD, lfirst ? left + 1 : left)));
+                    cur = MRT_REF(MRT_T_POD, lfirst ? left : left + 1);
+                    descend = true;
+                }
+                break;
+            }
+            case MRT_T_TRANSLATE: {   // scene_object.cpp:9-18
+                MrtF4 x = ld4(sc.xlate, idx);
+                if (cnt) cnt->xform++;
+                st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
+                st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
+                st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
+                st.push((uint32_t) ray.inside);
+                st.push(MRT_FRAME(MRT_F_XLATE_END, idx));
+                ray.o = ray.o - v3(x);
+                ray.inside = 0;
+                ray_set_dir(ray, ray.d);   // the ray ctor re-normalises
+                cur = f2u(x.w);
+                descend = true;
+                break;
+            }
+            case MRT_T_ROTATE_Y: {    // scene_object.cpp:70-98
+                MrtF4 r0 = ld4(sc.rot, 3 * idx), r1 = ld4(sc.rot, 3 * idx + 1);
+                ret = false;
+                if (f2u(r1.w)) {
+                    if (cnt) cnt->aabb++;
+                    if (!aabb_hit(r0, r1, ray, tmin, tmax)) break;
+                }
+                if (cnt) cnt->xform++;
+                MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
+                float sin_t = r2.x, cos_t = r2.y;
+                st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
+                st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
+                st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
+                st.push((uint32_t) ray.inside);
+                st.push(MRT_FRAME(MRT_F_ROT_END, idx));
+                V3 o = ray.o, d = ray.d;
+                o.x = cos_t * ray.o.x - sin_t * ray.o.z;
+                o.z = cos_t * ray.o.z + sin_t * ray.o.x;
+                d.x = cos_t * ray.d.x - sin_t * ray.d.z;
+                d.z = cos_t * ray.d.z + sin_t * ray.d.x;
+                ray.o = o;
+                ray.inside = 0;
+                ray_set_dir(ray, d);
+                cur = f2u(r0.w);
+                descend = true;
+                break;
+            }
+            case MRT_T_VOLUME: {      // volumes.cpp:5-36, first probe
+                MrtF4 vl = ld4(sc.vol, idx);
+                if (cnt) cnt->vol++;
+                st.push(MRT_FRAME(MRT_F_VOL1, idx));
+                main_tmax = tmax;
+                probe = true;
+                tmin = -FLT_MAX;
+                tmax = FLT_MAX;
+                cur = f2u(vl.x);
+                descend = true;
+                break;
+            }
+            default:
+                ret = false;
+                break;
+            }
+        }
+
+        // ----------------------------------------------------------- return
+        for (;;) {
+            if (st.sp == sp0) return ret && !probe;
+            uint32_t e = st.pop();
+            uint32_t tag = e >> 29;
+            if (tag == MRT_F_IF_MISS) {
+                if (ret) continue;
+                cur = e & 0x0FFFFFFFu;
+                break;
+            } else if (tag == MRT_F_LIST) {
+                // closest-hit loop over the children (scene_object.h:88-95); primitives inline
+                uint32_t ci = e & 0x0FFFFFFFu;
+                bool found = ((e >> 28) & 1u) | (ret ? 1u : 0u);
+                bool composite = false;
+                for (;;) {
+                    uint32_t c = ldu(sc.child, ci);
+                    uint32_t ctype = MRT_REF_TYPE(c);
+                    if (ctype == MRT_T_END) break;
+                    ci++;
+                    if (ctype == MRT_T_SPHERE) {
+                        if (cnt) cnt->sphere++;
+                        if (hit_sphere(sc, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
+                    } else if (ctype <= MRT_T_RECT_YZ) {
+                        if (cnt) cnt->rect++;
+                        if (hit_rect(sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
+                    } else {
+                        st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
+                        cur = c;
+                        composite = true;
+                        break;
+                    }
+                }
+                if (composite) break;
+                ret = found;
+                continue;
+            } else if (tag == MRT_F_XLATE_END || tag == MRT_F_ROT_END) {
+                ray.inside = (int) st.pop();
+                ray.inv.z = st.popf(); ray.inv.y = st.popf(); ray.inv.x = st.popf();
+                ray.d.z = st.popf(); ray.d.y = st.popf(); ray.d.x = st.popf();
+                ray.o.z = st.popf(); ray.o.y = st.popf(); ray.o.x = st.popf();
+                ray.mask = dir_mask(ray.d);
+                if (ret && !probe) {
+                    uint32_t idx = e & 0x0FFFFFFFu;
+                    if (tag == MRT_F_XLATE_END) {
+                        rec.p = rec.p + v3(ld4(sc.xlate, idx));
+                    } else {
+                        MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
+                        float sin_t = r2.x, cos_t = r2.y;
+                        V3 p = rec.p, n = rec.n;
+                        p.x = cos_t * rec.p.x + sin_t * rec.p.z;
+                        p.z = cos_t * rec.p.z - sin_t * rec.p.x;
+                        n.x = cos_t * rec.n.x + sin_t * rec.n.z;
+                        n.z = cos_t * rec.n.z - sin_t * rec.n.x;
+                        rec.p = p;
+                        rec.n = n;
+                    }
+                }
+                continue;
+            } else if (tag == MRT_F_VOL1) {
+                uint32_t idx = e & 0x0FFFFFFFu;
+                if (!ret) {
+                    probe = false; tmin = tmin0; tmax = main_tmax;
+                    continue;
+                }
+                vol_t1 = tmax;   // rec1.t
+                st.push(MRT_FRAME(MRT_F_VOL2, idx));
+                tmin = vol_t1 + 0.0001f;
+                tmax = FLT_MAX;
+                cur = f2u(ld4(sc.vol, idx).x);
+                break;
+            } else {   // MRT_F_VOL2
+                uint32_t idx = e & 0x0FFFFFFFu;
+                float t2 = tmax;
+                bool both = ret;
+                probe = false; tmin = tmin0; tmax = main_tmax;
+                ret = false;
+                if (!both) continue;
+                float t1 = vol_t1;
+                if (t1 < tmin) t1 = tmin;
+                if (t2 > tmax) t2 = tmax;
+                if (t1 >= t2) continue;
+                if (t1 < 0) t1 = 0;
+                MrtF4 vl = ld4(sc.vol, idx);
+                float inside_dist = (t2 - t1);
+                float hit_dist = -(fdiv(1, vl.y)) * logf(randf(rng));
+                if (hit_dist < inside_dist) {
+                    rec.t = t1 + hit_dist;
+                    rec.p = ray_eval(ray, rec.t);
+                    rec.n = v3(1, 0, 0);
+                    rec.mat = f2u(vl.z);
+                    tmax = rec.t;
+                    ret = true;
+                }
+                continue;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------- textures
+// texture.cpp:68-165
+MRT_HD float perlin_noise(const SceneView &sc, V3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int) fx, j = (int) fy, k = (int) fz;
+    int x0 = sc.perlin_perm[(i + 0) & 255], x1 = sc.perlin_perm[(i + 1) & 255];
+    int y0 = sc.perlin_perm[256 + ((j + 0) & 255)], y1 = sc.perlin_perm[256 + ((j + 1) & 255)];
+    int z0 = sc.perlin_perm[512 + ((k + 0) & 255)], z1 = sc.perlin_perm[512 + ((k + 1) & 255)];
+    float uu = u * u * (3 - 2 * u), vv = v * v * (3 - 2 * v), ww = w * w * (3 - 2 * w);
+    float acc = 0;
+#define MRT_PERLIN_CORNER(XI, YI, ZI, DI, DJ, DK)                                            \
+    {                                                                                         \
+        V3 c = v3(ld4(sc.perlin_vec, (uint32_t) ((XI) ^ (YI) ^ (ZI))));                       \
+        V3 wt = v3(u - (DI), v - (DJ), w - (DK));                                             \
+        float ax = (DI) ? uu : (1 - uu), ay = (DJ) ? vv : (1 - vv), az = (DK) ? ww : (1 - ww); \
+        acc += ax * ay * az * dot(c, wt);                                                     \
+    }
+    MRT_PERLIN_CORNER(x0, y0, z0, 0, 0, 0)
+    MRT_PERLIN_CORNER(x0, y0, z1, 0, 0, 1)
+    MRT_PERLIN_CORNER(x0, y1, z0, 0, 1, 0)
+    MRT_PERLIN_CORNER(x0, y1, z1, 0, 1, 1)
+    MRT_PERLIN_CORNER(x1, y0, z0, 1, 0, 0)
+    MRT_PERLIN_CORNER(x1, y0, z1, 1, 0, 1)
+    MRT_PERLIN_CORNER(x1, y1, z0, 1, 1, 0)
+    MRT_PERLIN_CORNER(x1, y1, z1, 1, 1, 1)
+#undef MRT_PERLIN_CORNER
+    return acc;
+}
+MRT_HD float perlin_turbulence(const SceneView &sc, V3 p) {   // depth 7, texture.cpp:153-165
+    float acc = 0;
+    float weight = 1.0f;
+    for (int i = 0; i < 7; i++) {
+        acc += weight * perlin_noise(sc, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(acc);
+}
+
+MRT_HD V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) {
+    for (;;) {
+        MrtF4 t = ld4(sc.tex, tex);
+        uint32_t kind = f2u(t.x);
+        if (kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);
+        if (kind == MRT_X_CHECKER) {   // texture.cpp:7-13
+            float s = t.w;
+            float sines = sinf(s * p.x) * sinf(s * p.y) * sinf(s * p.z);
+            tex = (sines < 0) ? f2u(t.z) : f2u(t.y);
+            continue;
+        }
+        if (kind == MRT_X_PERLIN) {    // texture.h:56-59
+            float turb = perlin_turbulence(sc, p * t.y);
+            return v3(1, 1, 1) * turb;
+        }
+        // image, texture.cpp:207-225
+        int32_t width = (int32_t) f2u(t.y), height = (int32_t) f2u(t.z);
+        int32_t i = (int32_t) (u * width);
+        int32_t j = (int32_t) ((1 - v) * height);
+        i = i < 0 ? 0 : (i > width - 1 ? width - 1 : i);
+        j = j < 0 ? 0 : (j > height - 1 ? height - 1 : j);
+        const uint8_t *px = sc.image + f2u(t.w) + ((size_t) i + (size_t) width * j) * 3;
+        const float f = (1.0f / 255.0f);
+        return v3((float) px[0], (float) px[1], (float) px[2]) * f;
+    }
+}
+
+// ----------------------------------------------------------------- light pdfs
+// object_list::pdf_value / pdf_generate over scene.biased_objects
+// (scene_object.h:64-77); sphere (sphere.cpp:63-79) and xz_rect (rect.cpp:92-107)
+// have pdfs, every other object the base-class defaults (scene_object.h:24-29).
+MRT_HD float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time) {
+    float sum = 0;
+    for (uint32_t i = 0; i < sc.n_lights; i++) {
+        uint32_t l = ldu(sc.lights, i);
+        uint32_t type = MRT_REF_TYPE(l), idx = MRT_REF_INDEX(l);
+        float pv = 0;
+        Hit rec;
+        if (type == MRT_T_RECT_XZ) {
+            Ray r = make_ray(origin, dir, 0.0f, 0);
+            if (hit_rect(sc, 1, idx, r, 0.001f, FLT_MAX, false, rec)) {
+                MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
+                float area = (q0.y - q0.x) * (q0.w - q0.z);
+                float dist_sq = rec.t * rec.t;
+                float cosine = fabsf(dot(dir, v3(0, q1.y, 0)));
+                pv = fdiv(dist_sq, (cosine * area));
+            }
+        } else if (type == MRT_T_SPHERE) {
+            Ray r = make_ray(origin, dir, time, 0);
+            if (hit_sphere(sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
+                MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
+                V3 cen = sphere_center(s0, s1, sc.sphere, idx, time);
+                float cos_theta_max = fsqrt(1 - fdiv(s0.w * s0.w, sdot(cen - origin)));
+                float solid_angle = 2 * MRT_PI_F * (1 - cos_theta_max);
+                pv = fdiv(1, solid_angle);
+            }
+        }
+        sum += pv;
+    }
+    return fdiv(sum, (float) sc.n_lights);
+}
+
+struct Onb { V3 u, v, w; };   // onb.h:19-27
+MRT_HD Onb make_onb(V3 n) {
+    Onb o;
+    o.w = n;
+    V3 a = (fabsf(n.x) > 0.9f) ? v3(0, 1, 0) : v3(1, 0, 0);
+    o.v = normalize(cross(o.w, a));
+    o.u = cross(o.w, o.v);
+    return o;
+}
+MRT_HD V3 onb_local(const Onb &o, V3 a) { return (a.x * o.u + a.y * o.v) + a.z * o.w; }
+
+MRT_HD V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rng) {
+    int i = (int) (randf(rng) * (float) sc.n_lights);
+    uint32_t l = ldu(sc.lights, (uint32_t) i);
+    uint32_t type = MRT_REF_TYPE(l), idx = MRT_REF_INDEX(l);
+    if (type == MRT_T_RECT_XZ) {
+        MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
+        float rx = randf(rng), rz = randf(rng);
+        V3 rnd = v3(q0.x + rx * (q0.y - q0.x), q1.x, q0.z + rz * (q0.w - q0.z));
+        return rnd - origin;
+    } else if (type == MRT_T_SPHERE) {
+        MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
+        V3 dir = sphere_center(s0, s1, sc.sphere, idx, time) - origin;
+        float dist_sq = sdot(dir);
+        Onb uvw = make_onb(normalize(dir));
+        return onb_local(uvw, random_towards_sphere(s0.w, dist_sq, rng));
+    }
+    return v3(1, 0, 0);
+}
+
+// --------------------------------------------------------------------- camera
+// camera.h:38-45
+MRT_HD Ray camera_get_ray(const MrtCamera &c, float s, float t, Rng &rng) {
+    V3 rd = c.lens_radius * random_in_disk(rng);
+    V3 cu = v3(c.u[0], c.u[1], c.u[2]), cv = v3(c.v[0], c.v[1], c.v[2]);
+    V3 offset = cu * rd.x + cv * rd.y;
+    float time = c.time0 + (c.time1 - c.time0) * randf(rng);
+    V3 origin = v3(c.origin[0], c.origin[1], c.origin[2]);
+    V3 ll = v3(c.llcorner[0], c.llcorner[1], c.llcorner[2]);
+    V3 horz = v3(c.horz[0], c.horz[1], c.horz[2]), vert = v3(c.vert[0], c.vert[1], c.vert[2]);
+    V3 dir = (((ll + s * horz) + t * vert) - origin) - offset;
+    return make_ray(origin + offset, dir, time, 0);
+}
+
+// ---------------------------------------------------------------------- trace
+// One path = the reference's recursive trace() (main.cpp:66-118) unrolled:
+//   L = e0 + w0 (e1 + w1 (...))   ->   L += T * e_k ; T *= w_k
+// with w = attenuation * scattering_pdf / pdf_v (main.cpp:102) or attenuation
+// (specular, main.cpp:83; emitted light is dropped there, as in the reference).
+struct Path {
+    Ray ray;
+    V3 T, L;
+    uint32_t depth;
+};
+
+// Shade one segment.  Returns true if the path continues.
+MRT_HD bool shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
+    if (!hit) {   // main.cpp:108-117
+        if (sc.sky) {
+            float t = 0.5f * (p.ray.d.y + 1.0f);
+            float a = 1.0f - t;
+            V3 bg = v3(a, a, a) + t * v3(0.5f, 0.7f, 1.0f);
+            p.L = p.L + p.T * bg;
+        }
+        return false;
+    }
+    MrtF4 m = ld4(sc.mat, rec.mat);
+    uint32_t kind = f2u(m.x) & 0xFFu;
+    uint32_t tex = f2u(m.y);
+    const Ray &r = p.ray;
+
+    if (kind == MRT_M_LIGHT) {   // material.h:190-199: emits towards the side the normal faces; never scatters
+        if (dot(rec.n, r.d) < 0.0f) {
+            V3 e = m.z * tex_sample(sc, tex, rec.u, rec.v, rec.p);
+            p.L = p.L + p.T * e;
+        }
+        return false;
+    }
+    if (!(p.depth < max_bounces)) return false;   // emitted == 0 for every non-light material
+
+    if (kind == MRT_M_METAL) {   // material.h:84-98
+        V3 att = tex_sample(sc, tex, rec.u, rec.v, rec.p);
+        float dp = 2.0f * dot(r.d, rec.n);
+        V3 reflected = r.d - (dp * rec.n);
+        V3 fuzz = (1 - m.z) * random_in_sphere(rng);
+        p.ray = make_ray(rec.p, reflected + fuzz, r.time, 0);
+        p.T = att * p.T;
+        p.depth++;
+        return true;
+    }
+    if (kind == MRT_M_DIELECTRIC) {   // material.h:106-175
+        float ref_index = m.z;
+        V3 fn;
+        float ni_over_nt;
+        float cosI = -dot(r.d, rec.n);
+        if (cosI < 0) { fn = neg(rec.n); ni_over_nt = ref_index; }
+        else          { fn = rec.n;      ni_over_nt = fdiv(1.0f, ref_index); }
+        // refract(), vec3.h:185-198
+        float ncosI = dot(r.d, fn);
+        float sinT2 = (ni_over_nt * ni_over_nt) * (1.0f - ncosI * ncosI);
+        float dp = 2.0f * dot(r.d, rec.n);
+        V3 reflected = r.d - (dp * rec.n);
+        V3 dir = reflected;
+        int inside = r.inside;
+        if (sinT2 <= 1.0f) {
+            float cosT = fsqrt(1.0f - sinT2);
+            float k = ni_over_nt * (-ncosI) - cosT;
+            V3 refracted = ni_over_nt * r.d + k * fn;
+            float cosine_schlick;
+            if (cosI < 0) cosine_schlick = fsqrt(1.0f - ni_over_nt * ni_over_nt * (1.0f - cosI * cosI));
+            else          cosine_schlick = cosI;
+            float r0 = fdiv(1 - ref_index, 1 + ref_index);
+            r0 = r0 * r0;
+            float reflect_prob = r0 + (1 - r0) * powf((1 - cosine_schlick), 5);
+            if (!(randf(rng) < reflect_prob)) {
+                if (cosI < 0) { inside--; if (inside < 0) inside = 0; }
+                else          { inside++; }
+                dir = refracted;
+            }
+        }
+        p.ray = make_ray(rec.p, dir, r.time, inside);
+        p.depth++;   // attenuation = (1,1,1)
+        return true;
+    }
+
+    // lambertian (material.h:40-53) / isotropic (material.h:64-73): pdf sampling, main.cpp:84-102
+    V3 att = tex_sample(sc, tex, rec.u, rec.v, rec.p);
+    const bool lambert = (kind == MRT_M_LAMBERTIAN);
+    Onb uvw;
+    if (lambert) uvw = make_onb(rec.n);
+    V3 dir;
+    bool use_light = false;
+    if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
+    if (use_light)    dir = light_pdf_generate(sc, rec.p, r.time, rng);
+    else if (lambert) dir = onb_local(uvw, random_cosine_direction(rng));
+    else              dir = random_in_sphere(rng);
+    Ray scattered = make_ray(rec.p, dir, r.time, 0);
+    float mat_pdf;
+    if (lambert) {   // cosine_pdf::value, pdf.h:24-30
+        float cosine = dot(scattered.d, uvw.w);
+        mat_pdf = (cosine > 0) ? fdiv(cosine, MRT_PI_F) : 0.0f;
+    } else {
+        mat_pdf = fdiv(1, (2 * MRT_PI_F));
+    }
+    float pdf_v = mat_pdf;
+    if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(sc, rec.p, scattered.d, r.time) + mat_pdf);
+    float spdf;
+    if (lambert) {   // lambertian::scattering_pdf
+        float cosine = dot(rec.n, scattered.d);
+        spdf = (cosine < 0) ? 0.0f : cosine * (1.0f / MRT_PI_F);
+    } else {
+        spdf = 1.0f / (2.0f * MRT_PI_F);
+    }
+    V3 w = (att * spdf) / pdf_v;
+    p.T = p.T * w;
+    p.ray = scattered;
+    p.depth++;
+    return true;
+}
+
+// A sample counts only if it is finite (main.cpp:163-165).  In the reference's nested
+// evaluation a non-finite weight (e.g. 0/0 when scattering_pdf == pdf_v == 0) poisons
+// the whole sample even if nothing is emitted further down the path (0 * NaN = NaN), so
+// the throughput is checked together with the radiance.
+MRT_HD bool path_sample_finite(const Path &p) {
+    return is_finite(p.L.x) && is_finite(p.L.y) && is_finite(p.L.z) && is_finite(p.T.x) && is_finite(p.T.y) && is_finite(p.T.z);
+}
+
+// Sub-pixel offset of sample s on the regular sqrt(N) x sqrt(N) grid (main.cpp:319-332)
+MRT_HD void sample_offset(uint32_t s, uint32_t sqrt_n, float *sx, float *sy) {
+    uint32_t i = s / sqrt_n, j = s - i * sqrt_n;
+    *sx = fdiv(i + 0.5f, (float) sqrt_n);
+    *sy = fdiv(j + 0.5f, (float) sqrt_n);
+}
+
+MRT_HD void path_begin(const SceneView &sc, Path &p, Rng &rng, uint32_t x, uint32_t y, uint32_t s, uint32_t sqrt_n,
+                       uint32_t width, uint32_t height, uint64_t seed) {
+    uint64_t stream = ((uint64_t) y * width + x) * ((uint64_t) sqrt_n * sqrt_n) + s;
+    rng_seed(rng, seed, stream);
+    float sx, sy;
+    sample_offset(s, sqrt_n, &sx, &sy);
+    float u = fdiv(x + sx, (float) width);    // main.cpp:156-157
+    float v = fdiv(y + sy, (float) height);
+    p.ray = camera_get_ray(sc.cam, u, v, rng);
+    p.T = v3(1, 1, 1);
+    p.L = v3(0, 0, 0);
+    p.depth = 0;
+}
+
+}  // namespace mrt
