@@ -1,0 +1,135 @@
+/* mrt_gpu.h -- C ABI of the B200 renderer for MiniRayTracer's bounce loop.
+ *
+ * The reference has no plugin / FFI interface: its renderer is entered by
+ * spawning worker threads on draw()/draw2() (main.cpp:138-243, spawned at
+ * main.cpp:378-382) with a `drawArgs` (main.cpp:127-135) that points at the
+ * scene graph (scene.h:19-23), the sample grid (main.cpp:319-332) and the
+ * global parameters (cmdline_parser.h:5-18); the workers write
+ * G_linearBackBuffer (main.cpp:58,175) and count rays in G_rayCounter
+ * (main.cpp:55,68); the main thread polls work_queue::getPercentDone
+ * (main.cpp:395).  This header is that seam as a C ABI: plain pointers and
+ * sizes, opaque handles, int status codes, no C++ or torch types.
+ *
+ * All functions return MRT_OK (0) or a negative MRT_E_* code; the message is
+ * available from mrt_last_error().  Nothing throws across the boundary (the
+ * reference is built with -fno-exceptions, clang/clang_build_linux.sh:27).
+ * All calls are expected from one host thread per scene handle.
+ */
+#ifndef MRT_GPU_H
+#define MRT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mrt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRT_OK 0
+#define MRT_E_INVALID (-1)  /* bad argument */
+#define MRT_E_CUDA (-2)     /* CUDA runtime error (no device, launch failure, ...) */
+#define MRT_E_SCENE (-3)    /* scene could not be built / flattened (missing asset, limits) */
+#define MRT_E_STATE (-4)    /* call order (e.g. readback before any render) */
+
+const char *mrt_last_error(void);
+
+/* ------------------------------------------------------------------ host side
+ * Replaces: ParseArgv/getParams (cmdline_parser.cpp:74-104) and select_scene
+ * (scene.cpp:27-49).  Host-only code: usable without a GPU. */
+
+/* MRT_Params (cmdline_parser.h:5-18) plus the options the new host adds. */
+typedef struct MrtParams {
+    uint32_t window_width, window_height;
+    uint32_t buffer_width, buffer_height;
+    uint32_t samples_per_pixel;
+    uint32_t tile_size;
+    uint32_t num_threads;
+    uint32_t max_bounces;
+    uint32_t scene_select;
+    uint32_t threading_mode;
+    float max_luminance;
+    uint32_t delay;
+    /* additions (not in the reference) */
+    uint32_t num_gpus;   /* -gpus  */
+    uint64_t seed;       /* -seed  : PCG32 initstate of the per-(pixel,sample) streams */
+    char out_path[512];  /* -out   : image file (.ppm tone-mapped, .pfm linear) */
+    char asset_dir[512]; /* -assets: directory holding earthmap.ppm and obj/ */
+} MrtParams;
+
+void mrt_params_default(MrtParams *p);
+/* Same options, defaults, range checks and warnings as ParseArgv (cmdline_parser.cpp:78-104).
+ * Returns 1 if -help/--help/-? was given (help text printed), 0 otherwise. */
+int mrt_params_parse(int argc, char **argv, MrtParams *p);
+
+typedef struct MrtHostScene MrtHostScene;
+/* scene: the reference's enum scenes value (scene.h:6-17), aspect = width/height. */
+int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHostScene **out);
+/* Flattened description (pointers stay valid until mrt_scene_free). */
+const MrtSceneDesc *mrt_scene_desc(const MrtHostScene *s);
+/* Canonical text dump of the scene graph (same format as the oracle's dump-scene). */
+int mrt_scene_dump(const MrtHostScene *s, const char *path);
+void mrt_scene_free(MrtHostScene *s);
+
+/* ----------------------------------------------------------------- device side
+ * Replaces: the draw()/draw2() worker threads and work_queue (work_queue.cpp). */
+
+typedef struct MrtDeviceInfo {
+    int device;
+    int sm_count;
+    int clock_khz;
+    int cc_major, cc_minor;
+    uint64_t total_mem;
+    char name[128];
+} MrtDeviceInfo;
+
+int mrt_gpu_init(int device, MrtDeviceInfo *info /* may be NULL */);
+
+typedef struct MrtScene MrtScene;
+/* Copies the flattened scene to the current device.  The description and everything it
+ * points to may be freed afterwards. */
+int mrt_gpu_scene_upload(const MrtSceneDesc *desc, MrtScene **out);
+/* Launch on this CUDA stream (a cudaStream_t passed as void*; NULL = default stream). */
+int mrt_gpu_set_stream(MrtScene *s, void *cuda_stream);
+/* Render into caller-owned device memory (width*height float4) instead of the library's own
+ * accumulator -- e.g. a tensor that is then sum-reduced across GPUs.  NULL unbinds. */
+int mrt_gpu_bind_accumulator(MrtScene *s, void *device_ptr, uint32_t width, uint32_t height);
+/* Asynchronously renders samples [sample_begin, sample_end) of every pixel into the
+ * accumulator: float4 = (sum of finite radiance samples, finite-sample count), row-major,
+ * y up like G_linearBackBuffer.  Replaces spawning draw() (main.cpp:378-382). */
+int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p);
+/* Progress in percent (work_queue::getPercentDone, main.cpp:395) and rays so far;
+ * never blocks. */
+int mrt_gpu_poll(MrtScene *s, float *pct_done, uint64_t *rays);
+/* Blocks until the last render has finished (thread join, main.cpp:491-493). */
+int mrt_gpu_wait(MrtScene *s);
+
+typedef struct MrtRenderStats {
+    uint64_t rays;       /* trace() calls = path segments (G_rayCounter, main.cpp:68) */
+    uint64_t paths;      /* (pixel, sample) pairs */
+    uint64_t nonfinite;  /* samples dropped by the finite check (main.cpp:163-165) */
+    float kernel_ms;     /* CUDA-event time of the render kernel on its stream */
+    uint32_t grid, block, smem_bytes, mode;
+} MrtRenderStats;
+/* Statistics of the last finished render (blocks like mrt_gpu_wait). */
+int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out);
+
+/* mean over finite samples + luminance clamp (main.cpp:168-173) on device buffers:
+ * out[i].xyz = clamp(acc[i].xyz / acc[i].w), out[i].w = acc[i].w.  In place is allowed. */
+int mrt_gpu_finalize_device(MrtScene *s, const void *acc_dev, void *out_dev, uint32_t width, uint32_t height,
+                            float max_luminance);
+/* Copies the accumulator (finalize = 0) or the finalised image (finalize = 1) to
+ * rgba_host (width*height*4 floats); blocks.  Replaces reading G_linearBackBuffer. */
+int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize);
+/* Adaptive logarithmic tone map + ARGB32 pack of the reference's preview loop
+ * (main.cpp:416-444, vec3.h:327-333) from the finalised image; argb_host: width*height uint32. */
+int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host);
+/* Requests the running render to stop early (G_isRunning = false, main.cpp:274). */
+int mrt_gpu_cancel(MrtScene *s);
+void mrt_gpu_destroy(MrtScene *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRT_GPU_H */

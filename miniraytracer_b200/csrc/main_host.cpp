@@ -1,0 +1,165 @@
+// Command-line front end: the reference's main() (main.cpp:283-498) with the
+// worker threads replaced by the GPU renderer behind the C ABI.  Same options
+// (cmdline_parser.cpp:90-104) plus -gpus/-seed/-assets/-out; headless (the SDL
+// preview of platform_linux.cpp is optional in the reference's design and SDL2
+// is not available here), so the "window title" statistics go to stdout and the
+// image goes to a file.  With -gpus N the samples per pixel are split across N
+// devices of this process and the accumulators are summed on the host (the
+// torch.distributed/NCCL path of bench.py is the multi-process equivalent).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mrt_gpu.h"
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int write_ppm(const char *path, const uint32_t *argb, uint32_t w, uint32_t h) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    fprintf(f, "P6\n%u %u\n255\n", w, h);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint32_t *row = argb + (size_t) (h - 1 - y) * w;   // buffer is y-up (platform_linux.cpp:84 flips at display)
+        for (uint32_t x = 0; x < w; x++) {
+            unsigned char px[3] = {(unsigned char) (row[x] >> 16), (unsigned char) (row[x] >> 8), (unsigned char) row[x]};
+            fwrite(px, 1, 3, f);
+        }
+    }
+    fclose(f);
+    return 0;
+}
+
+static int write_pfm(const char *path, const float *rgba, uint32_t w, uint32_t h) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    fprintf(f, "PF\n%u %u\n-1.0\n", w, h);   // little endian, bottom-to-top rows = our y-up order
+    for (size_t i = 0; i < (size_t) w * h; i++) fwrite(rgba + i * 4, sizeof(float), 3, f);
+    fclose(f);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    MrtParams p;
+    if (mrt_params_parse(argc, argv, &p)) return 0;
+    const uint32_t W = p.buffer_width, H = p.buffer_height;
+
+    double t0 = now_s();
+    MrtHostScene *hs = nullptr;
+    if (mrt_scene_create(p.scene_select, float(W) / float(H), p.asset_dir, &hs)) {
+        fprintf(stderr, "error: %s\n", mrt_last_error());
+        return 1;
+    }
+    printf("MiniRayTracer - Scene: %.0fms\n", 1000.0 * (now_s() - t0));
+
+    uint32_t sq = (uint32_t) sqrtf((float) p.samples_per_pixel);   // main.cpp:319-320
+    uint32_t N = sq * sq;
+    uint32_t G = p.num_gpus;
+    if (G > N) G = N;
+
+    std::vector<MrtScene *> scenes(G, nullptr);
+    MrtDeviceInfo info;
+    for (uint32_t g = 0; g < G; g++) {
+        if (mrt_gpu_init((int) g, &info) || mrt_gpu_scene_upload(mrt_scene_desc(hs), &scenes[g])) {
+            fprintf(stderr, "error: %s\n", mrt_last_error());
+            return 1;
+        }
+    }
+    double t1 = now_s();
+    for (uint32_t g = 0; g < G; g++) {
+        MrtRenderParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.width = W; rp.height = H; rp.samples = N;
+        rp.sample_begin = (uint32_t) ((uint64_t) N * g / G);
+        rp.sample_end = (uint32_t) ((uint64_t) N * (g + 1) / G);
+        rp.max_bounces = p.max_bounces;
+        rp.seed = p.seed;
+        rp.max_luminance = p.max_luminance;
+        mrt_gpu_init((int) g, nullptr);
+        if (mrt_gpu_render_async(scenes[g], &rp)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+    }
+    // poll loop (main.cpp:387-411)
+    for (;;) {
+        float pct_min = 100.0f;
+        for (uint32_t g = 0; g < G; g++) {
+            float pct = 0;
+            mrt_gpu_init((int) g, nullptr);
+            mrt_gpu_poll(scenes[g], &pct, nullptr);
+            if (pct < pct_min) pct_min = pct;
+        }
+        if (pct_min >= 100.0f) break;
+        double el = now_s() - t1;
+        fprintf(stderr, "\rTrace: %.2fs (%.0f%%)", el, pct_min);
+        std::this_thread::sleep_for(std::chrono::milliseconds(33));
+    }
+    uint64_t rays = 0, paths = 0, dropped = 0;
+    float kernel_ms = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        MrtRenderStats st;
+        mrt_gpu_init((int) g, nullptr);
+        if (mrt_gpu_stats(scenes[g], &st)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+        rays += st.rays; paths += st.paths; dropped += st.nonfinite;
+        if (st.kernel_ms > kernel_ms) kernel_ms = st.kernel_ms;
+    }
+    double secs = now_s() - t1;
+    fprintf(stderr, "\r");
+    printf("Trace: %.2fs - %.3f Mrays/s | %.6f us/ray | %.3f Mpaths/s | kernel %.1f ms | %llu samples dropped (non-finite)\n", secs,
+           rays * 1e-6 / secs, secs * 1e6 / (double) rays, paths * 1e-6 / secs, kernel_ms, (unsigned long long) dropped);
+
+    if (p.out_path[0]) {
+        std::vector<float> sum((size_t) W * H * 4, 0.0f), part((size_t) W * H * 4);
+        for (uint32_t g = 0; g < G; g++) {
+            mrt_gpu_init((int) g, nullptr);
+            if (mrt_gpu_readback(scenes[g], part.data(), 0)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+            for (size_t i = 0; i < sum.size(); i++) sum[i] += part[i];
+        }
+        // mean over finite samples + luminance clamp (main.cpp:168-173)
+        for (size_t i = 0; i < (size_t) W * H; i++) {
+            float *c = &sum[i * 4];
+            if (c[3] > 0) { c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3]; }
+            float lum = (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f;
+            if (lum > p.max_luminance) { float k = p.max_luminance / lum; c[0] *= k; c[1] *= k; c[2] *= k; }
+        }
+        size_t len = strlen(p.out_path);
+        int rc = 0;
+        if (len > 4 && !strcmp(p.out_path + len - 4, ".pfm")) {
+            rc = write_pfm(p.out_path, sum.data(), W, H);
+        } else if (G == 1) {
+            std::vector<uint32_t> argb((size_t) W * H);
+            mrt_gpu_init(0, nullptr);
+            if (mrt_gpu_tonemap(scenes[0], argb.data())) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+            rc = write_ppm(p.out_path, argb.data(), W, H);
+        } else {
+            // host tone map of the combined image (main.cpp:416-444)
+            float L_wmax = 0;
+            for (size_t i = 0; i < (size_t) W * H; i++) {
+                const float *c = &sum[i * 4];
+                L_wmax = std::fmax(L_wmax, (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f);
+            }
+            float bias = logf(0.7f) / logf(0.5f), invlogmax = 1.0f / log10f(L_wmax + 1.0f), invmax = 1.0f / L_wmax;
+            std::vector<uint32_t> argb((size_t) W * H);
+            for (size_t i = 0; i < (size_t) W * H; i++) {
+                const float *c = &sum[i * 4];
+                float lum = (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f;
+                float lum_new = (230.0f * 0.01f * invlogmax) * (logf(lum + 1.0f) / logf(2 + powf(lum * invmax, bias) * 8));
+                float d = lum + 0.00001f;
+                uint32_t r = (uint32_t) (std::fmin(lum_new * c[0] / d, 1.0f) * 255.99f);
+                uint32_t g = (uint32_t) (std::fmin(lum_new * c[1] / d, 1.0f) * 255.99f);
+                uint32_t b = (uint32_t) (std::fmin(lum_new * c[2] / d, 1.0f) * 255.99f);
+                argb[i] = (r << 16) | (g << 8) | b;
+            }
+            rc = write_ppm(p.out_path, argb.data(), W, H);
+        }
+        if (rc) { fprintf(stderr, "cannot write %s\n", p.out_path); return 1; }
+        printf("wrote %s\n", p.out_path);
+    }
+    for (uint32_t g = 0; g < G; g++) { mrt_gpu_init((int) g, nullptr); mrt_gpu_destroy(scenes[g]); }
+    mrt_scene_free(hs);
+    return 0;
+}

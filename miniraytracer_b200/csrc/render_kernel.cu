@@ -1,0 +1,606 @@
+// sm_100a render kernels + the device half of the C ABI (include/mrt_gpu.h).
+//
+// Work decomposition (replaces work_queue.cpp + the draw() loop nest,
+// main.cpp:138-188):
+//   * persistent warps: the grid is sized to the SM count x resident blocks and
+//     every warp pulls work from one global atomic ticket counter (one atomic
+//     per warp task, issued by lane 0 and broadcast with a shuffle);
+//   * a warp task is a small POOL of (pixel, sample) items that the 32 lanes
+//     drain cooperatively: whenever a lane's path terminates it is regenerated
+//     from the pool at the next warp-converged point (ballot + popc prefix), so
+//     lanes do not idle while the longest path of a batch finishes;
+//       mode W (>= 32 samples per pixel in this launch): pool = all samples of
+//              one pixel -> coherent primary rays; lane partial sums are
+//              combined with a fixed-order shuffle tree -> deterministic;
+//       mode P (< 32 samples): pool = a run of pixels; a lane owns a pixel and
+//              walks its samples in the reference's order (bit-identical sum);
+//   * per-thread traversal stacks live in shared memory, interleaved by lane
+//     (word k of lane l at [k*32 + l]) so pushes/pops are bank-conflict free.
+// Every accumulator element has exactly one writer: no float atomics, results
+// are reproducible run to run.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mrt_gpu.h"
+#include "trace_core.h"
+
+namespace mrt {
+
+void set_error(const std::string &msg);   // host_api.cpp
+
+struct RenderArgs {
+    SceneView sc;
+    uint32_t width, height, sqrt_n, s_begin, s_end, max_bounces;
+    uint64_t seed;
+    uint32_t accumulate;
+    uint32_t stack_words;
+    uint32_t n_tasks, pixels_per_task;
+    float4 *acc;
+    unsigned int *ticket;             // global task counter
+    unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
+    const volatile int *cancel;       // mapped host flag
+};
+
+constexpr int kBlock = 128;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// One segment of a live path: traverse, shade.  Returns true while the path continues.
+__device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng, Stack &st) {
+    Hit rec;
+    bool hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+    return shade(a.sc, p, hit, rec, a.max_bounces, rng);
+}
+
+// ------------------------------------------------------------------ mode W
+__global__ void __launch_bounds__(kBlock) render_pixel_per_warp(const RenderArgs a) {
+    extern __shared__ uint32_t smem_stack[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Stack st;
+    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
+    st.stride = 32u;
+    st.sp = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long rays = 0, nonfinite = 0;
+
+    for (;;) {
+        uint32_t pix = 0;
+        if (lane == 0) pix = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
+        pix = __shfl_sync(0xFFFFFFFFu, pix, 0);
+        if (pix >= a.n_tasks) break;
+        const uint32_t y = pix / a.width, x = pix - y * a.width;
+
+        uint32_t next_s = a.s_begin;   // warp-uniform pool cursor
+        bool alive = false;
+        Path p;
+        Rng rng;
+        float sr = 0, sg = 0, sb = 0, sc = 0;
+        for (;;) {
+            // regenerate terminated lanes from the pool
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !alive);
+            if (!alive) {
+                const uint32_t s = next_s + __popc(need & lt_mask);
+                if (s < a.s_end) {
+                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                    alive = true;
+                }
+            }
+            next_s = min(next_s + (uint32_t) __popc(need), a.s_end);
+            if (!__any_sync(0xFFFFFFFFu, alive)) break;
+            if (alive) {
+                rays++;
+                if (!path_step(a, p, rng, st)) {
+                    if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
+                    else nonfinite++;
+                    alive = false;
+                }
+            }
+        }
+        sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sc = warp_sum(sc);
+        if (lane == 0) {
+            float4 v = make_float4(sr, sg, sb, sc);
+            if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            a.acc[pix] = v;
+        }
+    }
+    // statistics: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[2], nonfinite);
+    }
+}
+
+// ------------------------------------------------------------------ mode P
+__global__ void __launch_bounds__(kBlock) render_pixel_per_lane(const RenderArgs a) {
+    extern __shared__ uint32_t smem_stack[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Stack st;
+    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
+    st.stride = 32u;
+    st.sp = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_pixels = a.width * a.height;
+    unsigned long long rays = 0, nonfinite = 0;
+
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= a.n_tasks) break;
+        uint32_t next_p = task * a.pixels_per_task;
+        const uint32_t end_p = min(next_p + a.pixels_per_task, n_pixels);
+
+        bool has_pixel = false, alive = false;
+        uint32_t pix = 0, x = 0, y = 0, s = 0;
+        Path p;
+        Rng rng;
+        float sr = 0, sg = 0, sb = 0, sc = 0;
+        for (;;) {
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !has_pixel);
+            if (!has_pixel) {
+                const uint32_t cand = next_p + __popc(need & lt_mask);
+                if (cand < end_p) {
+                    pix = cand;
+                    y = pix / a.width; x = pix - y * a.width;
+                    s = a.s_begin;
+                    sr = sg = sb = sc = 0;
+                    has_pixel = true;
+                }
+            }
+            next_p = min(next_p + (uint32_t) __popc(need), end_p);
+            if (!__any_sync(0xFFFFFFFFu, has_pixel)) break;
+            if (has_pixel) {
+                if (!alive) {
+                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                    alive = true;
+                }
+                rays++;
+                if (!path_step(a, p, rng, st)) {
+                    if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
+                    else nonfinite++;
+                    alive = false;
+                    if (++s == a.s_end) {
+                        float4 v = make_float4(sr, sg, sb, sc);
+                        if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        a.acc[pix] = v;
+                        has_pixel = false;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[2], nonfinite);
+    }
+}
+
+// --------------------------------------------------------------- finalize
+// color = sum / count ; luminance clamp (main.cpp:168-173, vec3.h:275-279)
+__global__ void finalize_kernel(const float4 *acc, float4 *out, uint32_t n, float max_lum) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = acc[i];
+    float r = 0, g = 0, b = 0;
+    if (a.w > 0) { r = __fdiv_rn(a.x, a.w); g = __fdiv_rn(a.y, a.w); b = __fdiv_rn(a.z, a.w); }
+    float lum = __fadd_rn(__fadd_rn(__fmul_rn(r, 0.212655f), __fmul_rn(g, 0.715158f)), __fmul_rn(b, 0.072187f));
+    if (lum > max_lum) {
+        float k = __fdiv_rn(max_lum, lum);
+        r = __fmul_rn(r, k); g = __fmul_rn(g, k); b = __fmul_rn(b, k);
+    }
+    out[i] = make_float4(r, g, b, a.w);
+}
+
+// --------------------------------------------------------------- tone map
+// Adaptive logarithmic mapping of the reference's preview loop (main.cpp:416-444)
+__global__ void max_luminance_kernel(const float4 *img, uint32_t n, unsigned int *max_bits) {
+    float m = 0.0f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 c = img[i];
+        float lum = __fadd_rn(__fadd_rn(__fmul_rn(c.x, 0.212655f), __fmul_rn(c.y, 0.715158f)), __fmul_rn(c.z, 0.072187f));
+        m = fmaxf(m, lum);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_uint(m));   // lum >= 0: uint order == float order
+}
+__global__ void tonemap_kernel(const float4 *img, uint32_t *argb, uint32_t n, const unsigned int *max_bits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float L_dmax = 230.0f;
+    const float bias = logf(0.7f) / logf(0.5f);
+    float L_wmax = __uint_as_float(*max_bits);
+    float invlogmax = 1.0f / log10f(L_wmax + 1.0f);
+    float invmax = 1.0f / L_wmax;
+    float4 c = img[i];
+    float lum = __fadd_rn(__fadd_rn(__fmul_rn(c.x, 0.212655f), __fmul_rn(c.y, 0.715158f)), __fmul_rn(c.z, 0.072187f));
+    float loglw = logf(lum + 1.0f);
+    float lum_new = (L_dmax * 0.01f * invlogmax) * (loglw / logf(2 + powf(lum * invmax, bias) * 8));
+    float d = lum + 0.00001f;
+    float r = fminf((lum_new * c.x) / d, 1.0f) * 255.99f;
+    float g = fminf((lum_new * c.y) / d, 1.0f) * 255.99f;
+    float b = fminf((lum_new * c.z) / d, 1.0f) * 255.99f;
+    argb[i] = ((uint32_t) r << 16) | ((uint32_t) g << 8) | (uint32_t) b;   // ARGB32, vec3.h:327-333
+}
+
+}  // namespace mrt
+
+// =========================================================================
+//                          C ABI (device half)
+// =========================================================================
+using namespace mrt;
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+            return MRT_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+struct MrtScene {
+    int device = 0;
+    int sm_count = 0;
+    std::vector<void *> allocs;
+    SceneView view;
+    uint32_t stack_words = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t poll_stream = nullptr;
+    // accumulator
+    float4 *own_acc = nullptr;
+    size_t own_acc_pixels = 0;
+    float4 *ext_acc = nullptr;
+    uint32_t ext_w = 0, ext_h = 0;
+    float4 *final_buf = nullptr;
+    size_t final_pixels = 0;
+    uint32_t *argb_buf = nullptr;
+    // control block
+    unsigned int *ticket = nullptr;
+    unsigned long long *counters = nullptr;
+    unsigned int *max_bits = nullptr;
+    int *cancel_host = nullptr;   // mapped pinned
+    int *cancel_dev = nullptr;
+    unsigned long long *poll_host = nullptr;   // pinned: [0] ticket [1] rays
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // last render
+    bool rendered = false;
+    MrtRenderParams last;
+    uint32_t last_tasks = 0, last_grid = 0, last_smem = 0, last_mode = 0;
+    float4 *last_acc = nullptr;
+};
+
+template <typename T>
+static int upload(MrtScene *s, const T *host, size_t count, const T **dev) {
+    *dev = nullptr;
+    if (!host || !count) return MRT_OK;
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
+    s->allocs.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *) d;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { set_error("mrt_gpu_init: no such CUDA device"); return MRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("mrt_gpu_init: kernels are built for sm_100a only, device is ") + prop.name);
+        return MRT_E_CUDA;
+    }
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->device = device;
+        info->sm_count = prop.multiProcessorCount;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        info->clock_khz = khz;
+        info->cc_major = prop.major;
+        info->cc_minor = prop.minor;
+        info->total_mem = prop.totalGlobalMem;
+        strncpy(info->name, prop.name, sizeof(info->name) - 1);
+    }
+    return MRT_OK;
+}
+
+extern "C" void mrt_gpu_destroy(MrtScene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->rendered) cudaStreamSynchronize(s->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->own_acc) cudaFree(s->own_acc);
+    if (s->final_buf) cudaFree(s->final_buf);
+    if (s->argb_buf) cudaFree(s->argb_buf);
+    if (s->ticket) cudaFree(s->ticket);
+    if (s->counters) cudaFree(s->counters);
+    if (s->max_bits) cudaFree(s->max_bits);
+    if (s->cancel_host) cudaFreeHost(s->cancel_host);
+    if (s->poll_host) cudaFreeHost(s->poll_host);
+    if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
+    if (!d || !out) { set_error("mrt_gpu_scene_upload: null argument"); return MRT_E_INVALID; }
+    *out = nullptr;
+    MrtScene *s = new (std::nothrow) MrtScene();
+    if (!s) { set_error("out of memory"); return MRT_E_INVALID; }
+    int rc = MRT_OK;
+    auto fail = [&](int code) { mrt_gpu_destroy(s); return code; };
+    if (cudaGetDevice(&s->device) != cudaSuccess) { set_error("no CUDA device (mrt_gpu_init not called?)"); return fail(MRT_E_CUDA); }
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    SceneView &v = s->view;
+    memset(&v, 0, sizeof(v));
+    if ((rc = upload(s, d->sphere, (size_t) d->n_sphere * 3, &v.sphere))) return fail(rc);
+    if ((rc = upload(s, d->rect, (size_t) d->n_rect * 2, &v.rect))) return fail(rc);
+    if ((rc = upload(s, d->list, (size_t) d->n_list * 2, &v.list))) return fail(rc);
+    if ((rc = upload(s, d->child, (size_t) d->n_child, &v.child))) return fail(rc);
+    if ((rc = upload(s, d->bvh, (size_t) d->n_bvh * 2, &v.bvh))) return fail(rc);
+    if ((rc = upload(s, d->pod, (size_t) d->n_pod * 2, &v.pod))) return fail(rc);
+    if ((rc = upload(s, d->tri, (size_t) d->n_tri * 3, &v.tri))) return fail(rc);
+    if ((rc = upload(s, d->trin, (size_t) d->n_tri * 3, &v.trin))) return fail(rc);
+    if ((rc = upload(s, d->xlate, (size_t) d->n_xlate, &v.xlate))) return fail(rc);
+    if ((rc = upload(s, d->rot, (size_t) d->n_rot * 3, &v.rot))) return fail(rc);
+    if ((rc = upload(s, d->vol, (size_t) d->n_vol, &v.vol))) return fail(rc);
+    if ((rc = upload(s, d->mat, (size_t) d->n_mat, &v.mat))) return fail(rc);
+    if ((rc = upload(s, d->tex, (size_t) d->n_tex, &v.tex))) return fail(rc);
+    if ((rc = upload(s, d->perlin_vec, d->perlin_vec ? 256 : 0, &v.perlin_vec))) return fail(rc);
+    if ((rc = upload(s, d->perlin_perm, d->perlin_perm ? 768 : 0, &v.perlin_perm))) return fail(rc);
+    if ((rc = upload(s, d->image, (size_t) d->n_image_bytes, &v.image))) return fail(rc);
+    if ((rc = upload(s, d->lights, (size_t) d->n_lights, &v.lights))) return fail(rc);
+    v.root = d->root;
+    v.n_lights = d->n_lights;
+    v.sky = d->sky;
+    v.cam = d->camera;
+    s->stack_words = d->stack_words ? d->stack_words : 64;
+
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
+        return true;
+    };
+    if (!cu(cudaMalloc(&s->ticket, sizeof(unsigned int)), "cudaMalloc ticket")) return fail(MRT_E_CUDA);
+    if (!cu(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long)), "cudaMalloc counters")) return fail(MRT_E_CUDA);
+    if (!cu(cudaMalloc(&s->max_bits, sizeof(unsigned int)), "cudaMalloc max_bits")) return fail(MRT_E_CUDA);
+    if (!cu(cudaHostAlloc(&s->cancel_host, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc cancel")) return fail(MRT_E_CUDA);
+    *s->cancel_host = 0;
+    if (!cu(cudaHostGetDevicePointer(&s->cancel_dev, s->cancel_host, 0), "cudaHostGetDevicePointer")) return fail(MRT_E_CUDA);
+    if (!cu(cudaHostAlloc(&s->poll_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc poll")) return fail(MRT_E_CUDA);
+    if (!cu(cudaStreamCreateWithFlags(&s->poll_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(MRT_E_CUDA);
+    if (!cu(cudaEventCreate(&s->ev0), "cudaEventCreate")) return fail(MRT_E_CUDA);
+    if (!cu(cudaEventCreate(&s->ev1), "cudaEventCreate")) return fail(MRT_E_CUDA);
+    *out = s;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_set_stream(MrtScene *s, void *cuda_stream) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    s->stream = (cudaStream_t) cuda_stream;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_bind_accumulator(MrtScene *s, void *device_ptr, uint32_t width, uint32_t height) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    if (device_ptr && ((uintptr_t) device_ptr & 15u)) { set_error("accumulator must be 16-byte aligned"); return MRT_E_INVALID; }
+    s->ext_acc = (float4 *) device_ptr;
+    s->ext_w = width;
+    s->ext_h = height;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
+    if (!s || !p) { set_error("mrt_gpu_render_async: null argument"); return MRT_E_INVALID; }
+    if (!p->width || !p->height || !p->samples || p->sample_begin >= p->sample_end || p->sample_end > p->samples) {
+        set_error("mrt_gpu_render_async: bad image size or sample range");
+        return MRT_E_INVALID;
+    }
+    uint32_t sq = (uint32_t) sqrtf((float) p->samples);
+    while ((uint64_t) (sq + 1) * (sq + 1) <= p->samples) sq++;
+    while ((uint64_t) sq * sq > p->samples) sq--;
+    if (sq * sq != p->samples) { set_error("mrt_gpu_render_async: samples must be a perfect square (main.cpp:319-320)"); return MRT_E_INVALID; }
+    const uint64_t n_pixels64 = (uint64_t) p->width * p->height;
+    if (n_pixels64 > 0x7FFFFFFFull) { set_error("image too large"); return MRT_E_INVALID; }
+    const uint32_t n_pixels = (uint32_t) n_pixels64;
+    CUDA_TRY(cudaSetDevice(s->device));
+
+    float4 *acc = nullptr;
+    if (s->ext_acc) {
+        if (s->ext_w != p->width || s->ext_h != p->height) { set_error("bound accumulator has a different size"); return MRT_E_INVALID; }
+        acc = s->ext_acc;
+    } else {
+        if (s->own_acc_pixels != n_pixels) {
+            if (s->own_acc) { cudaFree(s->own_acc); s->own_acc = nullptr; s->own_acc_pixels = 0; }
+            CUDA_TRY(cudaMalloc(&s->own_acc, (size_t) n_pixels * sizeof(float4)));
+            s->own_acc_pixels = n_pixels;
+            CUDA_TRY(cudaMemsetAsync(s->own_acc, 0, (size_t) n_pixels * sizeof(float4), s->stream));
+        }
+        acc = s->own_acc;
+    }
+
+    RenderArgs a;
+    a.sc = s->view;
+    a.width = p->width; a.height = p->height; a.sqrt_n = sq;
+    a.s_begin = p->sample_begin; a.s_end = p->sample_end; a.max_bounces = p->max_bounces;
+    a.seed = p->seed;
+    a.accumulate = (p->flags & MRT_RENDER_ACCUMULATE) ? 1u : 0u;
+    a.stack_words = s->stack_words;
+    a.acc = acc;
+    a.ticket = s->ticket;
+    a.counters = s->counters;
+    a.cancel = s->cancel_dev;
+    const uint32_t ns = p->sample_end - p->sample_begin;
+    const bool mode_w = ns >= 32;
+    a.pixels_per_task = mode_w ? 1u : 128u;
+    a.n_tasks = mode_w ? n_pixels : (n_pixels + a.pixels_per_task - 1) / a.pixels_per_task;
+
+    const size_t smem = (size_t) kWarpsPerBlock * s->stack_words * 32u * sizeof(uint32_t);
+    auto kernel = mode_w ? render_pixel_per_warp : render_pixel_per_lane;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int blocks_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, smem));
+    if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
+    uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
+    const uint32_t warps_needed = a.n_tasks;
+    const uint32_t blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (grid > blocks_needed) grid = blocks_needed;
+
+    *s->cancel_host = 0;
+    CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    kernel<<<grid, kBlock, smem, s->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    s->rendered = true;
+    s->last = *p;
+    s->last_tasks = a.n_tasks;
+    s->last_grid = grid;
+    s->last_smem = (uint32_t) smem;
+    s->last_mode = mode_w ? 1u : 0u;
+    s->last_acc = acc;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_poll(MrtScene *s, float *pct_done, uint64_t *rays) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    if (!s->rendered) { if (pct_done) *pct_done = 0; if (rays) *rays = 0; return MRT_OK; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (cudaEventQuery(s->ev1) == cudaSuccess) {
+        if (pct_done) *pct_done = 100.0f;
+        if (rays) {
+            CUDA_TRY(cudaMemcpyAsync(&s->poll_host[1], &s->counters[0], sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->poll_stream));
+            CUDA_TRY(cudaStreamSynchronize(s->poll_stream));
+            *rays = s->poll_host[1];
+        }
+        return MRT_OK;
+    }
+    s->poll_host[0] = 0;
+    CUDA_TRY(cudaMemcpyAsync(&s->poll_host[0], s->ticket, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->poll_stream));
+    CUDA_TRY(cudaMemcpyAsync(&s->poll_host[1], &s->counters[0], sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->poll_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->poll_stream));
+    // like work_queue_seq::getPercentDone (work_queue.cpp:142-149): tickets are taken at the start of work
+    double done = (double) (unsigned int) s->poll_host[0] - (double) s->last_grid * kWarpsPerBlock;
+    if (done < 0) done = 0;
+    double pct = s->last_tasks ? done * 100.0 / s->last_tasks : 0.0;
+    if (pct > 99.9) pct = 99.9;
+    if (pct_done) *pct_done = (float) pct;
+    if (rays) *rays = s->poll_host[1];   // warps add their counts when they retire
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_wait(MrtScene *s) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    if (!s->rendered) return MRT_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventSynchronize(s->ev1));
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
+    if (!s || !out) { set_error("mrt_gpu_stats: null argument"); return MRT_E_INVALID; }
+    if (!s->rendered) { set_error("mrt_gpu_stats: nothing rendered yet"); return MRT_E_STATE; }
+    int rc = mrt_gpu_wait(s);
+    if (rc) return rc;
+    unsigned long long c[4];
+    CUDA_TRY(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->rays = c[0];
+    out->paths = (uint64_t) s->last.width * s->last.height * (s->last.sample_end - s->last.sample_begin);
+    out->nonfinite = c[2];
+    CUDA_TRY(cudaEventElapsedTime(&out->kernel_ms, s->ev0, s->ev1));
+    out->grid = s->last_grid;
+    out->block = kBlock;
+    out->smem_bytes = s->last_smem;
+    out->mode = s->last_mode;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_finalize_device(MrtScene *s, const void *acc_dev, void *out_dev, uint32_t width, uint32_t height, float max_luminance) {
+    if (!s || !acc_dev || !out_dev) { set_error("mrt_gpu_finalize_device: null argument"); return MRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    uint32_t n = width * height;
+    finalize_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>((const float4 *) acc_dev, (float4 *) out_dev, n, max_luminance);
+    CUDA_TRY(cudaGetLastError());
+    return MRT_OK;
+}
+
+static int ensure_final(MrtScene *s, size_t n) {
+    if (s->final_pixels != n) {
+        if (s->final_buf) { cudaFree(s->final_buf); s->final_buf = nullptr; }
+        if (s->argb_buf) { cudaFree(s->argb_buf); s->argb_buf = nullptr; }
+        s->final_pixels = 0;
+        CUDA_TRY(cudaMalloc(&s->final_buf, n * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&s->argb_buf, n * sizeof(uint32_t)));
+        s->final_pixels = n;
+    }
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize) {
+    if (!s || !rgba_host) { set_error("mrt_gpu_readback: null argument"); return MRT_E_INVALID; }
+    if (!s->rendered) { set_error("mrt_gpu_readback: nothing rendered yet"); return MRT_E_STATE; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t) s->last.width * s->last.height;
+    const float4 *src = s->last_acc;
+    if (finalize) {
+        int rc = ensure_final(s, n);
+        if (rc) return rc;
+        rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last.width, s->last.height, s->last.max_luminance);
+        if (rc) return rc;
+        src = s->final_buf;
+    }
+    CUDA_TRY(cudaMemcpyAsync(rgba_host, src, n * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
+    if (!s || !argb_host) { set_error("mrt_gpu_tonemap: null argument"); return MRT_E_INVALID; }
+    if (!s->rendered) { set_error("mrt_gpu_tonemap: nothing rendered yet"); return MRT_E_STATE; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t) s->last.width * s->last.height;
+    int rc = ensure_final(s, n);
+    if (rc) return rc;
+    rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last.width, s->last.height, s->last.max_luminance);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->max_bits, 0, sizeof(unsigned int), s->stream));
+    max_luminance_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(s->final_buf, (uint32_t) n, s->max_bits);
+    tonemap_kernel<<<((uint32_t) n + 255) / 256, 256, 0, s->stream>>>(s->final_buf, s->argb_buf, (uint32_t) n, s->max_bits);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(argb_host, s->argb_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_cancel(MrtScene *s) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    if (s->cancel_host) {
+        *s->cancel_host = 1;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+    }
+    return MRT_OK;
+}

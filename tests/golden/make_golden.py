@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the reference oracle (oracle/_ref/mrt_ref, i.e. the
+reference's own code with per-(pixel, sample) RNG streams).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+golden_sceneS.npz : acc[h,w,4] float32 = (sum of finite samples, count), plus the render parameters.
+kat.txt           : PCG32 / sampler / Perlin known-answer vectors printed by `mrt_ref kat`.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_util  # noqa: E402
+
+W, H, SPP, DEPTH = 64, 36, 4, 32
+
+if __name__ == "__main__":
+    assert oracle_util.ensure_ref(), "oracle/_ref/mrt_ref not available"
+    for scene in range(9):
+        acc, meta = oracle_util.ref_render(scene, W, H, SPP, DEPTH)
+        np.savez_compressed(os.path.join(HERE, f"golden_scene{scene}.npz"), acc=acc, scene=scene, width=W, height=H,
+                            spp=SPP, depth=DEPTH, seed=np.uint64(oracle_util.DEFAULT_SEED), rays=np.uint64(meta["rays"]))
+        print("scene", scene, "rays", meta["rays"])
+    kat = oracle_util.ref_run(["kat"]).stdout
+    open(os.path.join(HERE, "kat.txt"), "w").write(kat)

@@ -1,0 +1,82 @@
+"""Test-side helpers around the oracle (oracle/_ref/mrt_ref = the patched reference renderer).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may use anything under oracle/.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "mrt_ref")
+ASSETS = os.path.join(ROOT, "assets")
+RUN_DIR = os.path.join(ASSETS, "run")
+CACHE = os.path.join(tempfile.gettempdir(), "mrt_oracle_cache")
+CSRC = os.path.join(ROOT, "miniraytracer_b200", "csrc")
+DEFAULT_SEED = 11350390909718046443
+
+
+def have_ref():
+    return os.path.exists(REF_BIN) and os.path.isdir(RUN_DIR)
+
+
+def ensure_ref():
+    """Build oracle/_ref/mrt_ref if the reference sources are available (this container only)."""
+    if not have_ref() and os.path.isdir(os.environ.get("MRT_REFERENCE_DIR", "/root/reference")):
+        subprocess.run([os.path.join(ROOT, "oracle", "build_ref.sh")], check=True)
+    return have_ref()
+
+
+def ref_run(args, **kw):
+    return subprocess.run([REF_BIN] + [str(a) for a in args], cwd=RUN_DIR, check=True, capture_output=True, text=True, **kw)
+
+
+def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0):
+    """Oracle render with per-(pixel, sample) RNG streams; returns (acc[h,w,4], meta). Cached in /tmp."""
+    from miniraytracer_b200.accfile import read_acc
+    os.makedirs(CACHE, exist_ok=True)
+    st = os.stat(REF_BIN)
+    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
+    path = os.path.join(CACHE, f"ref_{key}.bin")
+    if not os.path.exists(path):
+        tmp = path + f".{os.getpid()}.tmp"
+        ref_run(["render", "-scene", scene, "-width", width, "-height", height, "-samples", spp, "-depth", depth,
+                 "-seed", seed, "-s0", s0, "-s1", s1, "-threads", threads, "-out", tmp])
+        os.replace(tmp, path)
+    return read_acc(path)
+
+
+def ref_dump_scene(scene, width, height, out):
+    ref_run(["dump-scene", "-scene", scene, "-width", width, "-height", height, "-out", out])
+
+
+def build_emul():
+    """g++ build of the TEST-ONLY host emulation of the device tracer core."""
+    out_dir = os.path.join(ROOT, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "emul_render")
+    srcs = [os.path.join(ROOT, "tests", "host_emul", "emul_render.cpp")] + \
+           [os.path.join(CSRC, f) for f in ("scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "flatten.cpp")]
+    deps = srcs + [os.path.join(CSRC, "trace_core.h"), os.path.join(CSRC, "scene_graph.h"), os.path.join(ROOT, "include", "mrt_types.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-I", CSRC, "-I", os.path.join(ROOT, "include")] + srcs +
+                       ["-o", exe, "-lpthread"], check=True)
+    return exe
+
+
+def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0):
+    from miniraytracer_b200.accfile import read_acc
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        path = f.name
+    try:
+        r = subprocess.run([exe, "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(spp),
+                            "-depth", str(depth), "-seed", str(seed), "-s0", str(s0), "-s1", str(s1), "-assets", ASSETS,
+                            "-out", path, "-counters"], check=True, capture_output=True, text=True)
+        acc, meta = read_acc(path)
+        meta["counters"] = json.loads(r.stdout.strip().splitlines()[-1])
+        return acc, meta
+    finally:
+        os.unlink(path)

@@ -1,0 +1,35 @@
+"""Second correctness check of north_star: the converged image must have RMSE (vs the oracle) below the
+oracle's own seed-to-seed noise floor.  4096 spp at 1080p is hours of CPU, so the same statistical test is
+run at the highest spp the oracle finishes in about a minute: a GPU render with the oracle's seed is
+compared with an oracle render of a DIFFERENT seed (independent noise) -- if the GPU estimator were biased,
+RMSE(gpu_seedA, ref_seedB) would exceed RMSE(ref_seedA, ref_seedB)."""
+import numpy as np
+import pytest
+
+import oracle_util
+from miniraytracer_b200 import accfile, api
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not on this box")]
+
+
+def _rmse(a, b):
+    return float(np.sqrt(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2)))
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 128, 72, 1024), (7, 128, 72, 256)])
+def test_rmse_below_seed_noise_floor(scene, w, h, spp):
+    seed_a, seed_b = oracle_util.DEFAULT_SEED, 987654321
+    ref_a = accfile.finalize(oracle_util.ref_render(scene, w, h, spp, seed=seed_a)[0])
+    ref_b = accfile.finalize(oracle_util.ref_render(scene, w, h, spp, seed=seed_b)[0])
+    hs = api.HostScene(scene, w, h)
+    r = api.Renderer(hs, 0)
+    r.render_async(w, h, spp, seed=seed_a)
+    gpu_a = accfile.finalize(r.readback())
+    r.render_async(w, h, spp, seed=seed_b)
+    gpu_b = accfile.finalize(r.readback())
+    r.close(); hs.close()
+    floor = _rmse(ref_a, ref_b)
+    assert _rmse(gpu_a, ref_b) <= 1.05 * floor
+    assert _rmse(gpu_b, ref_a) <= 1.05 * floor
+    # and with identical streams the images coincide far below the noise floor
+    assert _rmse(gpu_a, ref_a) < 0.05 * floor

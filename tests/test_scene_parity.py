@@ -1,0 +1,64 @@
+"""Scene parity: the new host-side scene builder (scenes.cpp, scene_graph.cpp, obj_loader.cpp) must
+produce the reference's scene graph bit for bit -- object parameters, material/texture parameters,
+list order, bvh_node / pod_bvh topology, child order and node_order bytes."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util
+from miniraytracer_b200 import api
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", range(9))
+@pytest.mark.parametrize("size", [(1920, 1080), (500, 500)])
+def test_scene_dump_identical(scene, size, tmp_path):
+    w, h = size
+    ref = tmp_path / "ref.txt"
+    mine = tmp_path / "mine.txt"
+    oracle_util.ref_dump_scene(scene, w, h, str(ref))
+    hs = api.HostScene(scene, w, h)
+    hs.dump(mine)
+    hs.close()
+    a, b = ref.read_text(), mine.read_text()
+    assert len(a.splitlines()) > 3
+    assert a == b
+
+
+def test_perlin_tables_match_reference():
+    # texture.cpp:167-203 tables, built from the raw global generator state (pcg.cpp:40)
+    lines = open(os.path.join(GOLDEN, "kat.txt")).read().splitlines()
+    vec = [l for l in lines if l.startswith("perlin ranvec:")][0].split(":")[1].split()
+    ref_vec = np.array([[int(x, 16) for x in t.split(",")] for t in vec], dtype=np.uint32).view(np.float32)
+    perms = [np.array([int(x) for x in [l for l in lines if l.startswith(f"perlin perm_{a}:")][0].split(":")[1].split()])
+             for a in "xyz"]
+    hs = api.HostScene(3, 500, 500)   # spheres_perlin
+    d = hs.desc.contents
+    got_vec = np.array([[d.perlin_vec[i].x, d.perlin_vec[i].y, d.perlin_vec[i].z] for i in range(256)], dtype=np.float32)
+    got_perm = np.array([d.perlin_perm[i] for i in range(768)]).reshape(3, 256)
+    hs.close()
+    np.testing.assert_array_equal(got_vec, ref_vec)
+    for a in range(3):
+        np.testing.assert_array_equal(got_perm[a], perms[a])
+
+
+def test_flat_scene_shapes():
+    hs = api.HostScene(5, 1920, 1080)   # cornell box
+    d = hs.desc.contents
+    assert d.n_rect == 12 and d.n_sphere == 1 and d.n_xlate == 1 and d.n_rot == 1 and d.n_list == 2
+    assert d.n_lights == 1 and d.sky == 0
+    assert d.stack_words >= 2 * 11 + 2
+    hs.close()
+    hs = api.HostScene(0, 500, 500)
+    d = hs.desc.contents
+    assert d.sky == 1 and d.n_lights == 0 and d.n_sphere > 400 and d.n_bvh > 50
+    hs.close()
+
+
+def test_missing_asset_is_an_error(tmp_path):
+    with pytest.raises(api.MrtError):
+        api.HostScene(7, 640, 360, asset_dir=str(tmp_path))   # no earthmap.ppm there
