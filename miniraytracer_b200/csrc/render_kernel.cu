@@ -44,7 +44,7 @@ struct RenderArgs {
     float4 *acc;
     unsigned int *ticket;             // global task counter
     unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
-    const volatile int *cancel;       // mapped host flag
+    const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
 };
 
 constexpr int kBlock = 128;
@@ -277,8 +277,8 @@ struct MrtScene {
     unsigned int *ticket = nullptr;
     unsigned long long *counters = nullptr;
     unsigned int *max_bits = nullptr;
-    int *cancel_host = nullptr;   // mapped pinned
-    int *cancel_dev = nullptr;
+    int *cancel_dev = nullptr;    // device flag polled by lane 0 when it takes a ticket (L2 hit)
+    int *cancel_pinned = nullptr; // pinned staging word for the async write
     unsigned long long *poll_host = nullptr;   // pinned: [0] ticket [1] rays
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // last render
@@ -337,7 +337,8 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (s->ticket) cudaFree(s->ticket);
     if (s->counters) cudaFree(s->counters);
     if (s->max_bits) cudaFree(s->max_bits);
-    if (s->cancel_host) cudaFreeHost(s->cancel_host);
+    if (s->cancel_dev) cudaFree(s->cancel_dev);
+    if (s->cancel_pinned) cudaFreeHost(s->cancel_pinned);
     if (s->poll_host) cudaFreeHost(s->poll_host);
     if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -386,9 +387,9 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (!cu(cudaMalloc(&s->ticket, sizeof(unsigned int)), "cudaMalloc ticket")) return fail(MRT_E_CUDA);
     if (!cu(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long)), "cudaMalloc counters")) return fail(MRT_E_CUDA);
     if (!cu(cudaMalloc(&s->max_bits, sizeof(unsigned int)), "cudaMalloc max_bits")) return fail(MRT_E_CUDA);
-    if (!cu(cudaHostAlloc(&s->cancel_host, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc cancel")) return fail(MRT_E_CUDA);
-    *s->cancel_host = 0;
-    if (!cu(cudaHostGetDevicePointer(&s->cancel_dev, s->cancel_host, 0), "cudaHostGetDevicePointer")) return fail(MRT_E_CUDA);
+    if (!cu(cudaMalloc(&s->cancel_dev, sizeof(int)), "cudaMalloc cancel")) return fail(MRT_E_CUDA);
+    if (!cu(cudaMemset(s->cancel_dev, 0, sizeof(int)), "cudaMemset cancel")) return fail(MRT_E_CUDA);
+    if (!cu(cudaHostAlloc(&s->cancel_pinned, sizeof(int), cudaHostAllocDefault), "cudaHostAlloc cancel")) return fail(MRT_E_CUDA);
     if (!cu(cudaHostAlloc(&s->poll_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc poll")) return fail(MRT_E_CUDA);
     if (!cu(cudaStreamCreateWithFlags(&s->poll_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(MRT_E_CUDA);
     if (!cu(cudaEventCreate(&s->ev0), "cudaEventCreate")) return fail(MRT_E_CUDA);
@@ -468,7 +469,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     const uint32_t blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (grid > blocks_needed) grid = blocks_needed;
 
-    *s->cancel_host = 0;
+    CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
@@ -598,9 +599,11 @@ extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
 
 extern "C" int mrt_gpu_cancel(MrtScene *s) {
     if (!s) { set_error("null scene"); return MRT_E_INVALID; }
-    if (s->cancel_host) {
-        *s->cancel_host = 1;
-        std::atomic_thread_fence(std::memory_order_seq_cst);
+    if (s->cancel_dev && s->rendered) {
+        CUDA_TRY(cudaSetDevice(s->device));
+        *s->cancel_pinned = 1;
+        CUDA_TRY(cudaMemcpyAsync(s->cancel_dev, s->cancel_pinned, sizeof(int), cudaMemcpyHostToDevice, s->poll_stream));
+        CUDA_TRY(cudaStreamSynchronize(s->poll_stream));
     }
     return MRT_OK;
 }

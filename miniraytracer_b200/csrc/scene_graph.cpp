@@ -1,6 +1,7 @@
 // Host scene graph: constructors, bounding boxes and the two BVH builders of the
 // reference, restated over tagged nodes (see scene_graph.h).
 #include "scene_graph.h"
+#include "mrt_libm.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -76,7 +77,8 @@ Camera::Camera(H3 pos, H3 lookat, H3 up, float vfov, float aspect, float apertur
     time0 = t0;
     time1 = t1;
     float theta = H_RAD(vfov);
-    float height = 2.0f * tanf(theta / 2);
+    // the reference folds this tanf at compile time (correctly rounded); evaluate it the same way
+    float height = 2.0f * (float) tan((double) (theta / 2));
     float width = aspect * height;
     origin = pos;
     w = hnormalize(pos - lookat);
@@ -268,8 +270,8 @@ int SceneGraph::translate(int obj, H3 offset) {
 int SceneGraph::rotate_y(int obj, float angle) {   // scene_object.cpp:33-68
     Node n; n.kind = NodeKind::RotateY; n.child = obj;
     float radians = H_RAD(angle);
-    n.sin_theta = sinf(radians);
-    n.cos_theta = cosf(radians);
+    n.sin_theta = cr_sinf(radians);   // canonical libm, mrt_libm.h
+    n.cos_theta = cr_cosf(radians);
     Aabb bbox;
     n.has_box = bounding_box(obj, 0, 1, &bbox);
     if (!n.has_box) {
@@ -387,7 +389,7 @@ int SceneGraph::pod_bvh(std::vector<Triangle> &&tris, int mat) {
 M4 M4::identity() { M4 m{}; for (int i = 0; i < 4; i++) m.c[i][i] = 1; return m; }
 M4 M4::scale(float s) { M4 m{}; m.c[0][0] = s; m.c[1][1] = s; m.c[2][2] = s; m.c[3][3] = 1; return m; }
 M4 M4::rotate_y(float radians) {
-    float s = sinf(radians), c = cosf(radians);
+    float s = cr_sinf(radians), c = cr_cosf(radians);
     M4 m{};
     // Mat4(c,0,s,0, 0,1,0,0, -s,0,c,0, 0,0,0,1) given row-major, stored column-major
     m.c[0][0] = c;  m.c[1][0] = 0; m.c[2][0] = s; m.c[3][0] = 0;

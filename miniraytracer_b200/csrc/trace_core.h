@@ -12,10 +12,11 @@
 // floating-point expression keeps the reference's operation order, divisions
 // and square roots are IEEE (no rsqrt / reciprocal shortcuts), and the file is
 // compiled with -fmad=false (nvcc) / -ffp-contract=off (g++) so that no
-// multiply-add is fused.  Only libm calls (sinf cosf atan2f asinf logf powf)
-// may differ from the CPU by the library's ulp error.
+// multiply-add is fused.  The libm calls on the path (sinf cosf atan2f asinf
+// logf powf) use the correctly rounded values of mrt_libm.h on both sides.
 #pragma once
 #include "mrt_types.h"
+#include "mrt_libm.h"
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
@@ -141,8 +142,8 @@ MRT_HD V3 random_cosine_direction(Rng &r) {
     float z = fsqrt(1 - r2);
     float phi = 2 * MRT_PI_F * r1;
     float sr2 = fsqrt(r2);
-    float x = cosf(phi) * 2 * sr2;
-    float y = sinf(phi) * 2 * sr2;
+    float x = cr_cosf(phi) * 2 * sr2;
+    float y = cr_sinf(phi) * 2 * sr2;
     return v3(x, y, z);
 }
 // pcg.cpp:125-133
@@ -152,8 +153,8 @@ MRT_HD V3 random_towards_sphere(float radius, float dist_sq, Rng &r) {
     float z = 1 + r2 * (fsqrt(1 - fdiv(radius * radius, dist_sq)) - 1);
     float phi = 2 * MRT_PI_F * r1;
     float s = fsqrt(1 - z * z);
-    float x = cosf(phi) * s;
-    float y = sinf(phi) * s;
+    float x = cr_cosf(phi) * s;
+    float y = cr_sinf(phi) * s;
     return v3(x, y, z);
 }
 
@@ -254,8 +255,8 @@ MRT_HD V3 sphere_center(const MrtF4 &s0, const MrtF4 &s1, const MrtF4 *tab, uint
     return v3(s0);
 }
 MRT_HD void sphere_uv(V3 n, float *u, float *v) {  // sphere.cpp:6-11
-    float phi = atan2f(n.z, n.x);
-    float theta = asinf(n.y);
+    float phi = cr_atan2f(n.z, n.x);
+    float theta = cr_asinf(n.y);
     *u = 0.5f - phi * (1.0f / (2.0f * MRT_PI_F));
     *v = 0.5f + theta * (1.0f / MRT_PI_F);
 }
@@ -588,7 +589,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 if (t1 < 0) t1 = 0;
                 MrtF4 vl = ld4(sc.vol, idx);
                 float inside_dist = (t2 - t1);
-                float hit_dist = -(fdiv(1, vl.y)) * logf(randf(rng));
+                float hit_dist = -(fdiv(1, vl.y)) * cr_logf(randf(rng));
                 if (hit_dist < inside_dist) {
                     rec.t = t1 + hit_dist;
                     rec.p = ray_eval(ray, rec.t);
@@ -650,7 +651,7 @@ MRT_HD V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) 
         if (kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);
         if (kind == MRT_X_CHECKER) {   // texture.cpp:7-13
             float s = t.w;
-            float sines = sinf(s * p.x) * sinf(s * p.y) * sinf(s * p.z);
+            float sines = cr_sinf(s * p.x) * cr_sinf(s * p.y) * cr_sinf(s * p.z);
             tex = (sines < 0) ? f2u(t.z) : f2u(t.y);
             continue;
         }
@@ -818,7 +819,7 @@ MRT_HD bool shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32
             else          cosine_schlick = cosI;
             float r0 = fdiv(1 - ref_index, 1 + ref_index);
             r0 = r0 * r0;
-            float reflect_prob = r0 + (1 - r0) * powf((1 - cosine_schlick), 5);
+            float reflect_prob = r0 + (1 - r0) * cr_pow5f((1 - cosine_schlick));
             if (!(randf(rng) < reflect_prob)) {
                 if (cosI < 0) { inside--; if (inside < 0) inside = 0; }
                 else          { inside++; }

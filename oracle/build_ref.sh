@@ -24,6 +24,8 @@ TMP="$(mktemp -d /tmp/mrt_ref_build.XXXXXX)"
 trap 'rm -rf "$TMP"' EXIT
 python3 "$HERE/patch_reference.py" "$SRC" "$TMP"
 cp "$HERE/ref_harness.cpp" "$HERE/ref_platform_headless.cpp" "$TMP/"
+# libm canonicalisation (see cr_libm.cpp): separate TU, no builtin folding
+g++ -std=c++20 -O2 -ffp-contract=off -fno-builtin -c "$HERE/cr_libm.cpp" -o "$TMP/cr_libm.o"
 FILES=""
 for f in "$TMP"/*.cpp; do
     case "$(basename "$f")" in
@@ -34,7 +36,7 @@ done
 # -march=x86-64-v3: AVX2 class (mat4.h uses AVX-256); portable to the GPU box's host CPU.
 # -ffp-contract=off: no FMA contraction, so results do not depend on the optimiser.
 g++ -std=c++20 -O3 -march=x86-64-v3 -ffp-contract=off -fno-exceptions -fpermissive \
-    -D__cdecl= -D__stdcall= -w -I"$SRC/include" -I"$TMP" $FILES -o "$OUT/mrt_ref" -lpthread
+    -D__cdecl= -D__stdcall= -w -I"$SRC/include" -I"$TMP" $FILES "$TMP/cr_libm.o" -o "$OUT/mrt_ref" -lpthread -ldl
 # assets (data, not source)
 cp -f "$SRC/earthmap.jpg" "$ASSETS/earthmap.jpg"
 for o in bunny.obj Teapot3_no_vt.obj teapot.obj simple.obj pyramid.obj cylinder.obj; do

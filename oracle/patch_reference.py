@@ -20,7 +20,10 @@ Patch list:
      argument lists are sequenced explicitly left->right so that the oracle is
      compiler independent: pcg.cpp:73,115  rect.cpp:105
      scene.cpp:78,86,90,156,164,169,450.
-No arithmetic is changed by any patch.
+  P9 access only: `public:` added to pod_bvh (triangle.h:58) so the scene dump can read it.
+No arithmetic is changed by any source patch.  Separately, at LINK time, the six libm functions the path
+calls are bound to correctly rounded versions (oracle/cr_libm.cpp; rationale in
+miniraytracer_b200/csrc/mrt_libm.h); MRT_ORACLE_LIBM=host restores the host libm's own.
 """
 import os
 import re
