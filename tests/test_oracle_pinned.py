@@ -60,3 +60,26 @@ def test_oracle_reproduces_golden(scene):
         # libm may differ by an ulp between hosts; everything else is integer/IEEE exact
         res = accfile.compare(accfile.finalize(acc), accfile.finalize(g["acc"]), rel=1e-5)
         assert res["frac_ok"] >= 0.999, res
+
+
+@pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+def test_libm_canonicalisation_is_a_small_change():
+    """The oracle binds sinf/cosf/atan2f/asinf/logf/powf to correctly rounded versions (oracle/cr_libm.cpp).
+    With MRT_ORACLE_LIBM=host it uses the host libm's own float functions, i.e. the reference exactly as it
+    would run here.  The two renders must be the same image up to the rare 1-ulp disagreements of libm:
+    nearly all pixels bit-identical, the rest statistically equivalent."""
+    import subprocess, tempfile
+    outs = []
+    for mode in ("cr", "host"):
+        env = dict(os.environ)
+        env["MRT_ORACLE_LIBM"] = mode
+        path = os.path.join(tempfile.gettempdir(), f"mrt_libm_{mode}_{os.getpid()}.bin")
+        subprocess.run([oracle_util.REF_BIN, "render", "-scene", "0", "-width", "120", "-height", "120", "-samples", "16",
+                        "-out", path], cwd=oracle_util.RUN_DIR, env=env, check=True, capture_output=True)
+        outs.append(accfile.read_acc(path)[0])
+        os.unlink(path)
+    cr, host = outs
+    identical = float(np.all(cr == host, axis=-1).mean())
+    assert identical > 0.95, identical
+    res = accfile.compare(accfile.finalize(cr), accfile.finalize(host), rel=1e-4)
+    assert res["frac_ok"] > 0.995, res
