@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling only; marks the line as reduced)")
+    ap.add_argument("--size", default="", help="WxH override (profiling only; marks the line as reduced)")
     ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -173,6 +174,9 @@ def main():
     reduced = False
     if args.spp:
         spp, reduced = args.spp, True
+    if args.size:
+        W, H = (int(v) for v in args.size.lower().split("x"))
+        reduced = True
     N = api.grid_samples(spp)
     s_begin, s_end = mdist.shard_range(N, rank, world)
 
@@ -279,7 +283,7 @@ def main():
             "metric": "Mpath-samples/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (reference scene rebuilt from the reference's seed; no external data)",
-            "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload] + (" [REDUCED spp=%d]" % spp if reduced else ""),
+            "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload] + (" [REDUCED %dx%d spp=%d]" % (W, H, spp) if reduced else ""),
                        "scene": scene, "width": W, "height": H, "spp": N, "max_bounces": depth, "parallelism": f"spp-sharded x{world}",
                        "l2": "256 MB memset between timed steps; scene tables (<1 MB) are cache resident by design"},
             "grays_per_s": grays, "rays_per_path": float(rays_t.item()) / (paths_per_step * args.steps),

@@ -210,7 +210,6 @@ class Renderer:
         n = grid_samples(spp)
         p = RenderParams(width, height, n, sample_begin, n if sample_end is None else sample_end, depth, seed,
                          max_luminance, MRT_RENDER_ACCUMULATE if accumulate else 0)
-        _check(self._lib.mrt_gpu_init(self.device, None))
         _check(self._lib.mrt_gpu_render_async(self._h, C.byref(p)))
         self._size = (width, height)
         return p
@@ -233,6 +232,8 @@ class Renderer:
                                                  C.c_float(max_luminance)))
 
     def readback(self, finalize=False, out=None):
+        if self._size is None:
+            raise MrtError("readback before any render")
         w, h = self._size
         if out is None:
             out = np.empty((h, w, 4), dtype=np.float32)

@@ -22,6 +22,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -64,39 +65,63 @@ __device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng
 }
 
 // ------------------------------------------------------------------ mode W
-__global__ void __launch_bounds__(kBlock) render_pixel_per_warp(const RenderArgs a) {
+// Warp task = a chunk of `pixels_per_task` consecutive pixels x all samples of this launch, handed out as
+// one stream of items (pixel-major, sample-minor).  A lane keeps the running sum of the pixel it is
+// working on; when its next item belongs to another pixel it parks that partial sum in its own column of
+// a per-warp shared array part[k][lane] (one writer per element: a lane visits a pixel in one contiguous
+// period because items are handed out in increasing order).  At the end of the chunk every pixel's 32
+// partials are combined by a fixed-order shuffle tree.  The idle tail (lanes waiting for the last paths)
+// is paid once per chunk instead of once per pixel.
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const RenderArgs a) {
     extern __shared__ uint32_t smem_stack[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     Stack st;
     st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
     st.stride = 32u;
     st.sp = 0;
+    const uint32_t K = a.pixels_per_task;
+    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t ns = a.s_end - a.s_begin;
     unsigned long long rays = 0, nonfinite = 0;
 
     for (;;) {
-        uint32_t pix = 0;
-        if (lane == 0) pix = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
-        pix = __shfl_sync(0xFFFFFFFFu, pix, 0);
-        if (pix >= a.n_tasks) break;
-        const uint32_t y = pix / a.width, x = pix - y * a.width;
+        uint32_t task = 0;
+        if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= a.n_tasks) break;
+        const uint32_t pix0 = task * K;
+        const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
+        const uint32_t n_items = kp * ns;
+        for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        uint32_t next_s = a.s_begin;   // warp-uniform pool cursor
+        uint32_t next_i = 0;           // warp-uniform stream cursor
+        uint32_t cur_k = 0xFFFFFFFFu;  // pixel slot of this lane's running sum
         bool alive = false;
         Path p;
         Rng rng;
         float sr = 0, sg = 0, sb = 0, sc = 0;
         for (;;) {
-            // regenerate terminated lanes from the pool
+            // regenerate terminated lanes from the stream (warp-converged point)
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, !alive);
             if (!alive) {
-                const uint32_t s = next_s + __popc(need & lt_mask);
-                if (s < a.s_end) {
+                const uint32_t i = next_i + __popc(need & lt_mask);
+                if (i < n_items) {
+                    const uint32_t k = i / ns, s = a.s_begin + (i - k * ns);
+                    if (k != cur_k) {
+                        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
+                        sr = sg = sb = sc = 0;
+                        cur_k = k;
+                    }
+                    const uint32_t pix = pix0 + k;
+                    const uint32_t y = pix / a.width, x = pix - y * a.width;
                     path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
                     alive = true;
                 }
             }
-            next_s = min(next_s + (uint32_t) __popc(need), a.s_end);
+            next_i = min(next_i + (uint32_t) __popc(need), n_items);
             if (!__any_sync(0xFFFFFFFFu, alive)) break;
             if (alive) {
                 rays++;
@@ -107,12 +132,18 @@ __global__ void __launch_bounds__(kBlock) render_pixel_per_warp(const RenderArgs
                 }
             }
         }
-        sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sc = warp_sum(sc);
-        if (lane == 0) {
-            float4 v = make_float4(sr, sg, sb, sc);
-            if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            a.acc[pix] = v;
+        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
+        __syncwarp();
+        for (uint32_t k = 0; k < kp; k++) {
+            float4 v = part[k * 32u];
+            v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+            if (lane == 0) {
+                const uint32_t pix = pix0 + k;
+                if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                a.acc[pix] = v;
+            }
         }
+        __syncwarp();
     }
     // statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
@@ -126,7 +157,8 @@ __global__ void __launch_bounds__(kBlock) render_pixel_per_warp(const RenderArgs
 }
 
 // ------------------------------------------------------------------ mode P
-__global__ void __launch_bounds__(kBlock) render_pixel_per_lane(const RenderArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const RenderArgs a) {
     extern __shared__ uint32_t smem_stack[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     Stack st;
@@ -263,6 +295,8 @@ struct MrtScene {
     std::vector<void *> allocs;
     SceneView view;
     uint32_t stack_words = 0;
+    int min_blocks = 5;           // launch-bounds variant (MRT_MINB, tuning knob)
+    uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
     cudaStream_t stream = nullptr;
     cudaStream_t poll_stream = nullptr;
     // accumulator
@@ -305,13 +339,15 @@ extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
     CUDA_TRY(cudaGetDeviceCount(&n));
     if (device < 0 || device >= n) { set_error("mrt_gpu_init: no such CUDA device"); return MRT_E_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        set_error(std::string("mrt_gpu_init: kernels are built for sm_100a only, device is ") + prop.name);
+    int cc_major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    if (cc_major != 10) {
+        set_error("mrt_gpu_init: kernels are built for sm_100a only");
         return MRT_E_CUDA;
     }
-    if (info) {
+    if (info) {   // cudaGetDeviceProperties is slow (~100 ms): only on request
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         memset(info, 0, sizeof(*info));
         info->device = device;
         info->sm_count = prop.multiProcessorCount;
@@ -379,6 +415,8 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     v.sky = d->sky;
     v.cam = d->camera;
     s->stack_words = d->stack_words ? d->stack_words : 64;
+    if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
+    if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -455,18 +493,46 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.cancel = s->cancel_dev;
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
-    a.pixels_per_task = mode_w ? 1u : 128u;
-    a.n_tasks = mode_w ? n_pixels : (n_pixels + a.pixels_per_task - 1) / a.pixels_per_task;
-
-    const size_t smem = (size_t) kWarpsPerBlock * s->stack_words * 32u * sizeof(uint32_t);
-    auto kernel = mode_w ? render_pixel_per_warp : render_pixel_per_lane;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    // kernel variant: minimum resident blocks per SM the register allocation is bounded for
+    int minb = s->min_blocks;
+    typedef void (*kernel_t)(const RenderArgs);
+    kernel_t kernel = nullptr;
+    switch (minb) {
+    case 4: kernel = mode_w ? render_pixel_per_warp<4> : render_pixel_per_lane<4>; break;
+    case 6: kernel = mode_w ? render_pixel_per_warp<6> : render_pixel_per_lane<6>; break;
+    case 8: kernel = mode_w ? render_pixel_per_warp<8> : render_pixel_per_lane<8>; break;
+    default: minb = 5; kernel = mode_w ? render_pixel_per_warp<5> : render_pixel_per_lane<5>; break;
+    }
+    // choose the task size so that every resident warp gets several tasks (load balance) while the idle
+    // tail of a task stays small against its body
+    uint32_t K = 1;
+    size_t smem = 0;
     int blocks_per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, smem));
-    if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
+    uint32_t resident_warps = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        smem = (size_t) kWarpsPerBlock * s->stack_words * 32u * sizeof(uint32_t);
+        if (mode_w) smem += (size_t) kWarpsPerBlock * K * 32u * sizeof(float4);
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, smem));
+        if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
+        resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * kWarpsPerBlock;
+        if (pass == 1) break;
+        if (mode_w) {
+            K = s->chunk_pixels ? s->chunk_pixels : 8u;
+            while (K > 1 && n_pixels / K < 8u * resident_warps) K >>= 1;
+            if (K == 1) break;
+        } else {
+            K = s->chunk_pixels ? s->chunk_pixels : n_pixels / (8u * resident_warps);
+            K = (K + 31u) & ~31u;
+            if (K < 32u) K = 32u;
+            if (K > 1024u) K = 1024u;
+            break;
+        }
+    }
+    a.pixels_per_task = K;
+    a.n_tasks = (n_pixels + K - 1) / K;
     uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
-    const uint32_t warps_needed = a.n_tasks;
-    const uint32_t blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint32_t blocks_needed = (a.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (grid > blocks_needed) grid = blocks_needed;
 
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));

@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Tuning sweep on a GPU box: kernel variants (MRT_MINB launch bounds, MRT_CHUNK pixels per warp task) x workloads.
+Prints one JSON line per measurement (kernel time from CUDA events on the launch stream, after a warm-up)."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from miniraytracer_b200 import api  # noqa: E402
+
+CASES = {
+    "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
+    "C3": (6, 960, 540, 1024), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
+}
+
+
+def measure(case, minb, chunk, reps=2):
+    scene, w, h, spp = CASES[case]
+    os.environ["MRT_MINB"] = str(minb)
+    os.environ["MRT_CHUNK"] = str(chunk)
+    hs = api.HostScene(scene, w, h)
+    r = api.Renderer(hs, 0)
+    best = None
+    for i in range(reps + 1):
+        r.render_async(w, h, spp)
+        st = r.stats()
+        if i > 0 and (best is None or st["kernel_ms"] < best["kernel_ms"]):
+            best = st
+    r.close(); hs.close()
+    return {"case": case, "minb": minb, "chunk": chunk, "kernel_ms": best["kernel_ms"], "grays_per_s": best["rays"] / best["kernel_ms"] / 1e6,
+            "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"]}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="C2")
+    ap.add_argument("--minb", default="5")
+    ap.add_argument("--chunk", default="0")
+    args = ap.parse_args()
+    for case in args.cases.split(","):
+        for minb in args.minb.split(","):
+            for chunk in args.chunk.split(","):
+                print(json.dumps(measure(case, int(minb), int(chunk))), flush=True)
