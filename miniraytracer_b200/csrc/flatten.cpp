@@ -83,6 +83,31 @@ struct Flattener {
         }
     }
 
+    // The device traversal tests primitives only inside object_list loops (one copy of each hit test).
+    // A primitive referenced directly by a bvh_node (n <= 2 leaves, scene_object.h:297-303), a transform or
+    // a volume boundary is therefore wrapped into a box-less one-element list -- same result: the list
+    // passes (tmin, tmax) through and reports its only child's hit (scene_object.h:79-103).
+    std::map<uint32_t, uint32_t> wrap_memo;
+    static bool is_prim(uint32_t ref) { return MRT_REF_TYPE(ref) <= MRT_T_RECT_YZ; }
+    uint32_t wrap(uint32_t ref) {
+        if (!is_prim(ref)) return ref;
+        auto it = wrap_memo.find(ref);
+        if (it != wrap_memo.end()) return it->second;
+        uint32_t i = (uint32_t) o.list.size() / 2;
+        uint32_t first = (uint32_t) o.child.size();
+        o.child.push_back(ref);
+        o.child.push_back(MRT_REF_END);
+        o.list.push_back(f4(0, 0, 0, ubits(first)));
+        o.list.push_back(f4(0, 0, 0, ubits(1u)));
+        uint32_t w = MRT_REF(MRT_T_LIST, i);
+        wrap_memo[ref] = w;
+        return w;
+    }
+    bool node_is_prim(int id) const {
+        NodeKind k = g.nodes[id].kind;
+        return k == NodeKind::Sphere || k == NodeKind::RectXY || k == NodeKind::RectXZ || k == NodeKind::RectYZ;
+    }
+
     uint32_t node(int id) {
         auto it = memo.find(id);
         if (it != memo.end()) return it->second;
@@ -127,7 +152,7 @@ struct Flattener {
             break;
         }
         case NodeKind::Bvh: {
-            uint32_t l = node(n.left), r = node(n.right);
+            uint32_t l = wrap(node(n.left)), r = wrap(node(n.right));
             uint32_t i = (uint32_t) o.bvh.size() / 2;
             o.bvh.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(l | ((uint32_t) (n.order & 15u) << 28))));
             o.bvh.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, ubits(r | ((uint32_t) (n.order >> 4) << 28))));
@@ -135,14 +160,14 @@ struct Flattener {
             break;
         }
         case NodeKind::Translate: {
-            uint32_t c = node(n.child);
+            uint32_t c = wrap(node(n.child));
             uint32_t i = (uint32_t) o.xlate.size();
             o.xlate.push_back(f4(n.offset.x, n.offset.y, n.offset.z, ubits(c)));
             ref = MRT_REF(MRT_T_TRANSLATE, i);
             break;
         }
         case NodeKind::RotateY: {
-            uint32_t c = node(n.child);
+            uint32_t c = wrap(node(n.child));
             uint32_t i = (uint32_t) o.rot.size() / 3;
             o.rot.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(c)));
             o.rot.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, ubits(n.has_box ? 1u : 0u)));
@@ -152,7 +177,7 @@ struct Flattener {
         }
         case NodeKind::Volume: {
             if (contains_volume(n.child)) fail("a constant_volume boundary must not contain another constant_volume");
-            uint32_t b = node(n.child);
+            uint32_t b = wrap(node(n.child));
             uint32_t m = mat(n.mat);
             uint32_t i = (uint32_t) o.vol.size();
             o.vol.push_back(f4(ubits(b), n.density, ubits(m), 0));
@@ -193,6 +218,7 @@ struct Flattener {
         if (pn.prim_count) return 0;
         return 1 + std::max(pod_depth(m, pn.left), pod_depth(m, pn.left + 1));
     }
+    uint32_t depth_w(int id) const { return node_is_prim(id) ? 1u : depth(id); }   // wrapped primitives cost one LIST frame
     uint32_t depth(int id) const {
         const Node &n = g.nodes[id];
         switch (n.kind) {
@@ -202,10 +228,10 @@ struct Flattener {
             return 1 + d;
         }
         case NodeKind::Box: return depth(n.child);
-        case NodeKind::Bvh: return 1 + std::max(depth(n.left), depth(n.right));
+        case NodeKind::Bvh: return 1 + std::max(depth_w(n.left), depth_w(n.right));
         case NodeKind::Translate:
-        case NodeKind::RotateY: return 11 + depth(n.child);
-        case NodeKind::Volume: return 1 + depth(n.child);
+        case NodeKind::RotateY: return 11 + depth_w(n.child);
+        case NodeKind::Volume: return 1 + depth_w(n.child);
         case NodeKind::PodBvh: return pod_depth(g.meshes[n.mesh], 0);
         default: return 0;
         }
@@ -223,7 +249,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
         o.image.insert(o.image.end(), im.rgb.begin(), im.rgb.end());
         off += im.rgb.size();
     }
-    uint32_t root = fl.node(g.objects);
+    uint32_t root = fl.wrap(fl.node(g.objects));
     if (g.biased >= 0) {
         const Node &b = g.nodes[g.biased];
         if (b.kind != NodeKind::List) fl.fail("biased_objects must be an object_list");
@@ -247,7 +273,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     d.n_lights = (uint32_t) o.lights.size();
     d.lights = o.lights.data();
     d.sky = g.sky ? 1u : 0u;
-    d.stack_words = fl.depth(g.objects) + 2;
+    d.stack_words = fl.depth_w(g.objects) + 2;
     const Camera &c = g.camera;
     auto put = [](float *dst, H3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; };
     put(d.camera.origin, c.origin); put(d.camera.u, c.u); put(d.camera.v, c.v); put(d.camera.w, c.w);

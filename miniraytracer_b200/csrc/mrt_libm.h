@@ -15,16 +15,25 @@
 
 #ifdef __CUDACC__
 #define MRT_LIBM_HD __host__ __device__ __forceinline__
+#define MRT_LIBM_FN __host__ __device__ __noinline__   /* double-precision bodies are large: one copy each */
 #else
 #define MRT_LIBM_HD inline
+#define MRT_LIBM_FN inline
 #endif
 
 namespace mrt {
-MRT_LIBM_HD float cr_sinf(float x) { return (float) sin((double) x); }
-MRT_LIBM_HD float cr_cosf(float x) { return (float) cos((double) x); }
-MRT_LIBM_HD float cr_logf(float x) { return (float) log((double) x); }
-MRT_LIBM_HD float cr_atan2f(float y, float x) { return (float) atan2((double) y, (double) x); }
-MRT_LIBM_HD float cr_asinf(float x) { return (float) asin((double) x); }
+MRT_LIBM_FN float cr_sinf(float x) { return (float) sin((double) x); }
+MRT_LIBM_FN float cr_cosf(float x) { return (float) cos((double) x); }
+// sinf and cosf of the same argument (one shared range reduction); identical values to cr_sinf / cr_cosf
+MRT_LIBM_FN void cr_sincosf(float x, float *s, float *c) {
+    double ds, dc;
+    sincos((double) x, &ds, &dc);
+    *s = (float) ds;
+    *c = (float) dc;
+}
+MRT_LIBM_FN float cr_logf(float x) { return (float) log((double) x); }
+MRT_LIBM_FN float cr_atan2f(float y, float x) { return (float) atan2((double) y, (double) x); }
+MRT_LIBM_FN float cr_asinf(float x) { return (float) asin((double) x); }
 // powf(x, 5): x^5 with three double multiplications (<= 1.5 ulp of double before the single rounding)
 MRT_LIBM_HD float cr_pow5f(float x) {
     double d = (double) x;

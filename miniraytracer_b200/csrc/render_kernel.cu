@@ -60,8 +60,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One segment of a live path: traverse, shade.  Returns true while the path continues.
 __device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng, Stack &st) {
     Hit rec;
+    path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
     bool hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
-    return shade(a.sc, p, hit, rec, a.max_bounces, rng);
+    return path_shade(a.sc, p, hit, rec, a.max_bounces, rng);
 }
 
 // ------------------------------------------------------------------ mode W

@@ -24,8 +24,13 @@
 
 #ifdef __CUDACC__
 #define MRT_HD __host__ __device__ __forceinline__
+// Everything is inlined (ABI calls would force Ray/Hit through local memory); the hot loop is kept
+// inside the instruction cache by giving every large piece exactly ONE call site (ncu round 1: 55 % of
+// warp stalls were stall_no_inst with 154 KB of SASS from duplicated inlined bodies).
+#define MRT_FN __host__ __device__ __forceinline__
 #else
 #define MRT_HD inline
+#define MRT_FN inline
 #endif
 
 namespace mrt {
@@ -136,14 +141,16 @@ MRT_HD V3 random_in_disk(Rng &r) {
     return p;
 }
 // pcg.cpp:87-95 (the factor 2 on x,y is the reference's)
-MRT_HD V3 random_cosine_direction(Rng &r) {
+MRT_FN V3 random_cosine_direction(Rng &r) {
     float r1 = randf(r);
     float r2 = randf(r);
     float z = fsqrt(1 - r2);
     float phi = 2 * MRT_PI_F * r1;
     float sr2 = fsqrt(r2);
-    float x = cr_cosf(phi) * 2 * sr2;
-    float y = cr_sinf(phi) * 2 * sr2;
+    float sn, cs;
+    cr_sincosf(phi, &sn, &cs);
+    float x = cs * 2 * sr2;
+    float y = sn * 2 * sr2;
     return v3(x, y, z);
 }
 // pcg.cpp:125-133
@@ -153,8 +160,10 @@ MRT_HD V3 random_towards_sphere(float radius, float dist_sq, Rng &r) {
     float z = 1 + r2 * (fsqrt(1 - fdiv(radius * radius, dist_sq)) - 1);
     float phi = 2 * MRT_PI_F * r1;
     float s = fsqrt(1 - z * z);
-    float x = cr_cosf(phi) * s;
-    float y = cr_sinf(phi) * s;
+    float sn, cs;
+    cr_sincosf(phi, &sn, &cs);
+    float x = cs * s;
+    float y = sn * s;
     return v3(x, y, z);
 }
 
@@ -170,17 +179,20 @@ MRT_HD uint32_t dir_mask(V3 d) {
     uint32_t X = f2u(d.x) >> 31, Y = f2u(d.y) >> 31, Z = f2u(d.z) >> 31;
     return 1u << (Z | (Y << 1) | (X << 2));
 }
-MRT_HD void ray_set_dir(Ray &r, V3 dir) {  // direction is normalised by the ctor (ray.h:30)
+MRT_FN void ray_set_dir(Ray &r, V3 dir) {  // direction is normalised by the ctor (ray.h:30)
     r.d = normalize(dir);
     r.inv = v3(fdiv(1.0f, r.d.x), fdiv(1.0f, r.d.y), fdiv(1.0f, r.d.z));
     r.mask = dir_mask(r.d);
 }
-MRT_HD Ray make_ray(V3 o, V3 dir, float time, int inside) {
+// ray for a primitive self-test (pdf_value): only origin + normalised direction are used
+MRT_HD Ray make_probe_ray(V3 o, V3 dir, float time) {
     Ray r;
     r.o = o;
     r.time = time;
-    r.inside = inside;
-    ray_set_dir(r, dir);
+    r.inside = 0;
+    r.d = normalize(dir);
+    r.inv = v3(0, 0, 0);
+    r.mask = 0;
     return r;
 }
 MRT_HD V3 ray_eval(const Ray &r, float t) { return r.o + t * r.d; }
@@ -254,14 +266,14 @@ MRT_HD V3 sphere_center(const MrtF4 &s0, const MrtF4 &s1, const MrtF4 *tab, uint
     }
     return v3(s0);
 }
-MRT_HD void sphere_uv(V3 n, float *u, float *v) {  // sphere.cpp:6-11
+MRT_FN void sphere_uv(V3 n, float *u, float *v) {  // sphere.cpp:6-11
     float phi = cr_atan2f(n.z, n.x);
     float theta = cr_asinf(n.y);
     *u = 0.5f - phi * (1.0f / (2.0f * MRT_PI_F));
     *v = 0.5f + theta * (1.0f / MRT_PI_F);
 }
 // sphere.cpp:13-46.  full=false: only the distance is wanted (volume boundary probe).
-MRT_HD bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+MRT_FN bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
     MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
     V3 cen = sphere_center(s0, s1, sc.sphere, idx, r.time);
     float radius = s0.w;
@@ -320,7 +332,7 @@ MRT_HD bool hit_rect(const SceneView &sc, uint32_t axis, uint32_t idx, const Ray
 }
 
 // triangle.cpp:222-266 (Moeller-Trumbore path; NEW_INTERSECT is off, common.h:7)
-MRT_HD bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
     MrtF4 tm = ld4(sc.tri, 3 * idx), tu = ld4(sc.tri, 3 * idx + 1), tv = ld4(sc.tri, 3 * idx + 2);
     V3 u = v3(tu), v = v3(tv);
     V3 pvec = cross(r.d, v);
@@ -383,18 +395,6 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
             descend = false;
             const uint32_t type = MRT_REF_TYPE(cur), idx = MRT_REF_INDEX(cur);
             switch (type) {
-            case MRT_T_SPHERE:
-                if (cnt) cnt->sphere++;
-                ret = hit_sphere(sc, idx, ray, tmin, tmax, !probe, rec);
-                if (ret) tmax = rec.t;
-                break;
-            case MRT_T_RECT_XY:
-            case MRT_T_RECT_XZ:
-            case MRT_T_RECT_YZ:
-                if (cnt) cnt->rect++;
-                ret = hit_rect(sc, type - MRT_T_RECT_XY, idx, ray, tmin, tmax, !probe, rec);
-                if (ret) tmax = rec.t;
-                break;
             case MRT_T_LIST: {
                 MrtF4 l0 = ld4(sc.list, 2 * idx), l1 = ld4(sc.list, 2 * idx + 1);
                 ret = false;
@@ -445,44 +445,42 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 }
                 break;
             }
-            case MRT_T_TRANSLATE: {   // scene_object.cpp:9-18
-                MrtF4 x = ld4(sc.xlate, idx);
-                if (cnt) cnt->xform++;
-                st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
-                st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
-                st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
-                st.push((uint32_t) ray.inside);
-                st.push(MRT_FRAME(MRT_F_XLATE_END, idx));
-                ray.o = ray.o - v3(x);
-                ray.inside = 0;
-                ray_set_dir(ray, ray.d);   // the ray ctor re-normalises
-                cur = f2u(x.w);
-                descend = true;
-                break;
-            }
+            case MRT_T_TRANSLATE:     // scene_object.cpp:9-18
             case MRT_T_ROTATE_Y: {    // scene_object.cpp:70-98
-                MrtF4 r0 = ld4(sc.rot, 3 * idx), r1 = ld4(sc.rot, 3 * idx + 1);
                 ret = false;
-                if (f2u(r1.w)) {
-                    if (cnt) cnt->aabb++;
-                    if (!aabb_hit(r0, r1, ray, tmin, tmax)) break;
+                MrtF4 r0, r2;
+                if (type == MRT_T_ROTATE_Y) {
+                    r0 = ld4(sc.rot, 3 * idx);
+                    MrtF4 r1 = ld4(sc.rot, 3 * idx + 1);
+                    if (f2u(r1.w)) {   // bbox pre-test
+                        if (cnt) cnt->aabb++;
+                        if (!aabb_hit(r0, r1, ray, tmin, tmax)) break;
+                    }
+                    r2 = ld4(sc.rot, 3 * idx + 2);
+                } else {
+                    r0 = ld4(sc.xlate, idx);
+                    r2 = r0;
                 }
                 if (cnt) cnt->xform++;
-                MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
-                float sin_t = r2.x, cos_t = r2.y;
                 st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
                 st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
                 st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
                 st.push((uint32_t) ray.inside);
-                st.push(MRT_FRAME(MRT_F_ROT_END, idx));
-                V3 o = ray.o, d = ray.d;
-                o.x = cos_t * ray.o.x - sin_t * ray.o.z;
-                o.z = cos_t * ray.o.z + sin_t * ray.o.x;
-                d.x = cos_t * ray.d.x - sin_t * ray.d.z;
-                d.z = cos_t * ray.d.z + sin_t * ray.d.x;
-                ray.o = o;
+                st.push(MRT_FRAME(type == MRT_T_ROTATE_Y ? MRT_F_ROT_END : MRT_F_XLATE_END, idx));
+                V3 d = ray.d;
+                if (type == MRT_T_ROTATE_Y) {
+                    const float sin_t = r2.x, cos_t = r2.y;
+                    V3 o = ray.o;
+                    o.x = cos_t * ray.o.x - sin_t * ray.o.z;
+                    o.z = cos_t * ray.o.z + sin_t * ray.o.x;
+                    d.x = cos_t * ray.d.x - sin_t * ray.d.z;
+                    d.z = cos_t * ray.d.z + sin_t * ray.d.x;
+                    ray.o = o;
+                } else {
+                    ray.o = ray.o - v3(r0);
+                }
                 ray.inside = 0;
-                ray_set_dir(ray, d);
+                ray_set_dir(ray, d);   // the ray ctor re-normalises (ray.h:30); isInside resets to 0
                 cur = f2u(r0.w);
                 descend = true;
                 break;
@@ -633,7 +631,7 @@ MRT_HD float perlin_noise(const SceneView &sc, V3 p) {
 #undef MRT_PERLIN_CORNER
     return acc;
 }
-MRT_HD float perlin_turbulence(const SceneView &sc, V3 p) {   // depth 7, texture.cpp:153-165
+MRT_FN float perlin_turbulence(const SceneView &sc, V3 p) {   // depth 7, texture.cpp:153-165
     float acc = 0;
     float weight = 1.0f;
     for (int i = 0; i < 7; i++) {
@@ -644,14 +642,21 @@ MRT_HD float perlin_turbulence(const SceneView &sc, V3 p) {   // depth 7, textur
     return fabsf(acc);
 }
 
-MRT_HD V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) {
+MRT_FN V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) {
     for (;;) {
         MrtF4 t = ld4(sc.tex, tex);
         uint32_t kind = f2u(t.x);
         if (kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);
         if (kind == MRT_X_CHECKER) {   // texture.cpp:7-13
             float s = t.w;
-            float sines = cr_sinf(s * p.x) * cr_sinf(s * p.y) * cr_sinf(s * p.z);
+            float sines = 1.0f;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+            for (int a = 0; a < 3; a++) {   // one copy of the double-precision sine body; (sx * sy) * sz
+                float v = cr_sinf(s * (a == 0 ? p.x : (a == 1 ? p.y : p.z)));
+                sines = (a == 0) ? v : sines * v;
+            }
             tex = (sines < 0) ? f2u(t.z) : f2u(t.y);
             continue;
         }
@@ -675,7 +680,7 @@ MRT_HD V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) 
 // object_list::pdf_value / pdf_generate over scene.biased_objects
 // (scene_object.h:64-77); sphere (sphere.cpp:63-79) and xz_rect (rect.cpp:92-107)
 // have pdfs, every other object the base-class defaults (scene_object.h:24-29).
-MRT_HD float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time) {
+MRT_FN float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time) {
     float sum = 0;
     for (uint32_t i = 0; i < sc.n_lights; i++) {
         uint32_t l = ldu(sc.lights, i);
@@ -683,7 +688,7 @@ MRT_HD float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time)
         float pv = 0;
         Hit rec;
         if (type == MRT_T_RECT_XZ) {
-            Ray r = make_ray(origin, dir, 0.0f, 0);
+            Ray r = make_probe_ray(origin, dir, 0.0f);
             if (hit_rect(sc, 1, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
                 float area = (q0.y - q0.x) * (q0.w - q0.z);
@@ -692,7 +697,7 @@ MRT_HD float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time)
                 pv = fdiv(dist_sq, (cosine * area));
             }
         } else if (type == MRT_T_SPHERE) {
-            Ray r = make_ray(origin, dir, time, 0);
+            Ray r = make_probe_ray(origin, dir, time);
             if (hit_sphere(sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
                 V3 cen = sphere_center(s0, s1, sc.sphere, idx, time);
@@ -717,7 +722,7 @@ MRT_HD Onb make_onb(V3 n) {
 }
 MRT_HD V3 onb_local(const Onb &o, V3 a) { return (a.x * o.u + a.y * o.v) + a.z * o.w; }
 
-MRT_HD V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rng) {
+MRT_FN V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rng) {
     int i = (int) (randf(rng) * (float) sc.n_lights);
     uint32_t l = ldu(sc.lights, (uint32_t) i);
     uint32_t type = MRT_REF_TYPE(l), idx = MRT_REF_INDEX(l);
@@ -736,9 +741,39 @@ MRT_HD V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rn
     return v3(1, 0, 0);
 }
 
-// --------------------------------------------------------------------- camera
-// camera.h:38-45
-MRT_HD Ray camera_get_ray(const MrtCamera &c, float s, float t, Rng &rng) {
+// ---------------------------------------------------------------------- trace
+// One path = the reference's recursive trace() (main.cpp:66-118) unrolled:
+//   L = e0 + w0 (e1 + w1 (...))   ->   L += T * e_k ; T *= w_k
+// with w = attenuation * scattering_pdf / pdf_v (main.cpp:102) or attenuation
+// (specular, main.cpp:83; emitted light is dropped there, as in the reference).
+//
+// The per-segment work is arranged in phases so that every large piece of code has
+// exactly one call site (instruction-cache footprint) and so that all lanes of a warp
+// run the same phase at the same time:
+//   A  path_begin    : camera ray of a new (pixel, sample)          -- raw direction
+//   B  path_advance  : normalise the raw direction (THE ray constructor, ray.h:30)
+//   C                : weight of the previous diffuse bounce: pdf_v, scattering_pdf (main.cpp:88-102)
+//   D  intersect     : scene.hit
+//   E  path_shade    : emission, material scatter -> raw direction of the next segment
+struct Path {
+    Ray ray;        // between E and B, ray.d holds the raw (un-normalised) direction
+    V3 T, L;
+    uint32_t depth;
+    uint32_t pending;   // 0: nothing deferred; 1: lambertian bounce; 2: isotropic bounce
+    V3 p_att, p_n;      // attenuation and surface normal of the deferred bounce
+};
+
+// A: camera::get_ray (camera.h:38-45) for sample s of pixel (x, y); regular sub-pixel grid (main.cpp:319-332,156-157)
+MRT_HD void path_begin(const SceneView &sc, Path &p, Rng &rng, uint32_t x, uint32_t y, uint32_t s, uint32_t sqrt_n,
+                       uint32_t width, uint32_t height, uint64_t seed) {
+    uint64_t stream = ((uint64_t) y * width + x) * ((uint64_t) sqrt_n * sqrt_n) + s;
+    rng_seed(rng, seed, stream);
+    uint32_t i = s / sqrt_n, j = s - i * sqrt_n;
+    float sx = fdiv(i + 0.5f, (float) sqrt_n);
+    float sy = fdiv(j + 0.5f, (float) sqrt_n);
+    float u = fdiv(x + sx, (float) width);
+    float v = fdiv(y + sy, (float) height);
+    const MrtCamera &c = sc.cam;
     V3 rd = c.lens_radius * random_in_disk(rng);
     V3 cu = v3(c.u[0], c.u[1], c.u[2]), cv = v3(c.v[0], c.v[1], c.v[2]);
     V3 offset = cu * rd.x + cv * rd.y;
@@ -746,23 +781,40 @@ MRT_HD Ray camera_get_ray(const MrtCamera &c, float s, float t, Rng &rng) {
     V3 origin = v3(c.origin[0], c.origin[1], c.origin[2]);
     V3 ll = v3(c.llcorner[0], c.llcorner[1], c.llcorner[2]);
     V3 horz = v3(c.horz[0], c.horz[1], c.horz[2]), vert = v3(c.vert[0], c.vert[1], c.vert[2]);
-    V3 dir = (((ll + s * horz) + t * vert) - origin) - offset;
-    return make_ray(origin + offset, dir, time, 0);
+    p.ray.o = origin + offset;
+    p.ray.d = (((ll + u * horz) + v * vert) - origin) - offset;
+    p.ray.time = time;
+    p.ray.inside = 0;
+    p.T = v3(1, 1, 1);
+    p.L = v3(0, 0, 0);
+    p.depth = 0;
+    p.pending = 0;
 }
 
-// ---------------------------------------------------------------------- trace
-// One path = the reference's recursive trace() (main.cpp:66-118) unrolled:
-//   L = e0 + w0 (e1 + w1 (...))   ->   L += T * e_k ; T *= w_k
-// with w = attenuation * scattering_pdf / pdf_v (main.cpp:102) or attenuation
-// (specular, main.cpp:83; emitted light is dropped there, as in the reference).
-struct Path {
-    Ray ray;
-    V3 T, L;
-    uint32_t depth;
-};
+// B + C
+MRT_HD void path_advance(const SceneView &sc, Path &p) {
+    ray_set_dir(p.ray, p.ray.d);
+    if (p.pending) {
+        const V3 d = p.ray.d;
+        float mat_pdf, spdf;
+        if (p.pending == 1) {
+            float cosine = dot(d, p.p_n);                    // cosine_pdf::value (pdf.h:24-30); uvw.w == n
+            mat_pdf = (cosine > 0) ? fdiv(cosine, MRT_PI_F) : 0.0f;
+            spdf = (cosine < 0) ? 0.0f : cosine * (1.0f / MRT_PI_F);   // lambertian::scattering_pdf (material.h:40-46)
+        } else {
+            mat_pdf = fdiv(1, (2 * MRT_PI_F));               // isotropic_pdf::value (pdf.h:41-43)
+            spdf = 1.0f / (2.0f * MRT_PI_F);                 // isotropic::scattering_pdf (material.h:64-66)
+        }
+        float pdf_v = mat_pdf;
+        if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(sc, p.ray.o, d, p.ray.time) + mat_pdf);   // mix_pdf::value
+        V3 w = (p.p_att * spdf) / pdf_v;
+        p.T = p.T * w;
+        p.pending = 0;
+    }
+}
 
-// Shade one segment.  Returns true if the path continues.
-MRT_HD bool shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
+// E: returns true if the path continues (p.ray then holds the next origin and the raw direction)
+MRT_HD bool path_shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
     if (!hit) {   // main.cpp:108-117
         if (sc.sky) {
             float t = 0.5f * (p.ray.d.y + 1.0f);
@@ -773,95 +825,72 @@ MRT_HD bool shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32
         return false;
     }
     MrtF4 m = ld4(sc.mat, rec.mat);
-    uint32_t kind = f2u(m.x) & 0xFFu;
-    uint32_t tex = f2u(m.y);
+    const uint32_t kind = f2u(m.x) & 0xFFu;
     const Ray &r = p.ray;
-
-    if (kind == MRT_M_LIGHT) {   // material.h:190-199: emits towards the side the normal faces; never scatters
-        if (dot(rec.n, r.d) < 0.0f) {
-            V3 e = m.z * tex_sample(sc, tex, rec.u, rec.v, rec.p);
-            p.L = p.L + p.T * e;
-        }
+    // a light emits only towards the side its normal faces and never scatters (material.h:190-199);
+    // every other material emits nothing, so hitting the bounce limit ends the path with no contribution
+    if (kind == MRT_M_LIGHT ? !(dot(rec.n, r.d) < 0.0f) : !(p.depth < max_bounces)) return false;
+    V3 texv = v3(1, 1, 1);
+    if (kind != MRT_M_DIELECTRIC) texv = tex_sample(sc, f2u(m.y), rec.u, rec.v, rec.p);   // albedo / emissive
+    if (kind == MRT_M_LIGHT) {
+        p.L = p.L + p.T * (m.z * texv);
         return false;
     }
-    if (!(p.depth < max_bounces)) return false;   // emitted == 0 for every non-light material
-
-    if (kind == MRT_M_METAL) {   // material.h:84-98
-        V3 att = tex_sample(sc, tex, rec.u, rec.v, rec.p);
-        float dp = 2.0f * dot(r.d, rec.n);
-        V3 reflected = r.d - (dp * rec.n);
-        V3 fuzz = (1 - m.z) * random_in_sphere(rng);
-        p.ray = make_ray(rec.p, reflected + fuzz, r.time, 0);
-        p.T = att * p.T;
-        p.depth++;
-        return true;
-    }
-    if (kind == MRT_M_DIELECTRIC) {   // material.h:106-175
-        float ref_index = m.z;
-        V3 fn;
-        float ni_over_nt;
-        float cosI = -dot(r.d, rec.n);
-        if (cosI < 0) { fn = neg(rec.n); ni_over_nt = ref_index; }
-        else          { fn = rec.n;      ni_over_nt = fdiv(1.0f, ref_index); }
-        // refract(), vec3.h:185-198
-        float ncosI = dot(r.d, fn);
-        float sinT2 = (ni_over_nt * ni_over_nt) * (1.0f - ncosI * ncosI);
-        float dp = 2.0f * dot(r.d, rec.n);
-        V3 reflected = r.d - (dp * rec.n);
-        V3 dir = reflected;
-        int inside = r.inside;
-        if (sinT2 <= 1.0f) {
-            float cosT = fsqrt(1.0f - sinT2);
-            float k = ni_over_nt * (-ncosI) - cosT;
-            V3 refracted = ni_over_nt * r.d + k * fn;
-            float cosine_schlick;
-            if (cosI < 0) cosine_schlick = fsqrt(1.0f - ni_over_nt * ni_over_nt * (1.0f - cosI * cosI));
-            else          cosine_schlick = cosI;
-            float r0 = fdiv(1 - ref_index, 1 + ref_index);
-            r0 = r0 * r0;
-            float reflect_prob = r0 + (1 - r0) * cr_pow5f((1 - cosine_schlick));
-            if (!(randf(rng) < reflect_prob)) {
-                if (cosI < 0) { inside--; if (inside < 0) inside = 0; }
-                else          { inside++; }
-                dir = refracted;
+    V3 dir;
+    int inside = 0;
+    if (kind == MRT_M_METAL || kind == MRT_M_DIELECTRIC) {
+        float dp = 2.0f * dot(r.d, rec.n);          // reflect(), vec3.h:178-181
+        dir = r.d - (dp * rec.n);
+        if (kind == MRT_M_METAL) {                  // material.h:84-98
+            dir = dir + (1 - m.z) * random_in_sphere(rng);
+            p.T = texv * p.T;
+        } else {                                    // material.h:106-175
+            float ref_index = m.z;
+            V3 fn;
+            float ni_over_nt;
+            float cosI = -dot(r.d, rec.n);
+            if (cosI < 0) { fn = neg(rec.n); ni_over_nt = ref_index; }
+            else          { fn = rec.n;      ni_over_nt = fdiv(1.0f, ref_index); }
+            float ncosI = dot(r.d, fn);             // refract(), vec3.h:185-198
+            float sinT2 = (ni_over_nt * ni_over_nt) * (1.0f - ncosI * ncosI);
+            inside = r.inside;
+            if (sinT2 <= 1.0f) {
+                float cosT = fsqrt(1.0f - sinT2);
+                float k = ni_over_nt * (-ncosI) - cosT;
+                float cosine_schlick;
+                if (cosI < 0) cosine_schlick = fsqrt(1.0f - ni_over_nt * ni_over_nt * (1.0f - cosI * cosI));
+                else          cosine_schlick = cosI;
+                float r0 = fdiv(1 - ref_index, 1 + ref_index);   // fresnel_schlick, material.h:106-110
+                r0 = r0 * r0;
+                float reflect_prob = r0 + (1 - r0) * cr_pow5f((1 - cosine_schlick));
+                if (!(randf(rng) < reflect_prob)) {
+                    if (cosI < 0) { inside--; if (inside < 0) inside = 0; }
+                    else          { inside++; }
+                    dir = ni_over_nt * r.d + k * fn;
+                }
             }
         }
-        p.ray = make_ray(rec.p, dir, r.time, inside);
-        p.depth++;   // attenuation = (1,1,1)
-        return true;
-    }
-
-    // lambertian (material.h:40-53) / isotropic (material.h:64-73): pdf sampling, main.cpp:84-102
-    V3 att = tex_sample(sc, tex, rec.u, rec.v, rec.p);
-    const bool lambert = (kind == MRT_M_LAMBERTIAN);
-    Onb uvw;
-    if (lambert) uvw = make_onb(rec.n);
-    V3 dir;
-    bool use_light = false;
-    if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
-    if (use_light)    dir = light_pdf_generate(sc, rec.p, r.time, rng);
-    else if (lambert) dir = onb_local(uvw, random_cosine_direction(rng));
-    else              dir = random_in_sphere(rng);
-    Ray scattered = make_ray(rec.p, dir, r.time, 0);
-    float mat_pdf;
-    if (lambert) {   // cosine_pdf::value, pdf.h:24-30
-        float cosine = dot(scattered.d, uvw.w);
-        mat_pdf = (cosine > 0) ? fdiv(cosine, MRT_PI_F) : 0.0f;
     } else {
-        mat_pdf = fdiv(1, (2 * MRT_PI_F));
+        // lambertian (material.h:40-53) / isotropic (material.h:64-73): direction from the mixture pdf
+        // (main.cpp:84-92); its weight needs the NORMALISED direction and is applied in path_advance
+        const bool lambert = (kind == MRT_M_LAMBERTIAN);
+        bool use_light = false;
+        if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
+        if (use_light) {
+            dir = light_pdf_generate(sc, rec.p, r.time, rng);
+        } else if (lambert) {
+            Onb uvw = make_onb(rec.n);
+            dir = onb_local(uvw, random_cosine_direction(rng));
+        } else {
+            dir = random_in_sphere(rng);
+        }
+        p.pending = lambert ? 1u : 2u;
+        p.p_att = texv;
+        p.p_n = rec.n;
     }
-    float pdf_v = mat_pdf;
-    if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(sc, rec.p, scattered.d, r.time) + mat_pdf);
-    float spdf;
-    if (lambert) {   // lambertian::scattering_pdf
-        float cosine = dot(rec.n, scattered.d);
-        spdf = (cosine < 0) ? 0.0f : cosine * (1.0f / MRT_PI_F);
-    } else {
-        spdf = 1.0f / (2.0f * MRT_PI_F);
-    }
-    V3 w = (att * spdf) / pdf_v;
-    p.T = p.T * w;
-    p.ray = scattered;
+    p.ray.o = rec.p;
+    p.ray.d = dir;
+    p.ray.inside = inside;
     p.depth++;
     return true;
 }
@@ -872,27 +901,6 @@ MRT_HD bool shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32
 // the throughput is checked together with the radiance.
 MRT_HD bool path_sample_finite(const Path &p) {
     return is_finite(p.L.x) && is_finite(p.L.y) && is_finite(p.L.z) && is_finite(p.T.x) && is_finite(p.T.y) && is_finite(p.T.z);
-}
-
-// Sub-pixel offset of sample s on the regular sqrt(N) x sqrt(N) grid (main.cpp:319-332)
-MRT_HD void sample_offset(uint32_t s, uint32_t sqrt_n, float *sx, float *sy) {
-    uint32_t i = s / sqrt_n, j = s - i * sqrt_n;
-    *sx = fdiv(i + 0.5f, (float) sqrt_n);
-    *sy = fdiv(j + 0.5f, (float) sqrt_n);
-}
-
-MRT_HD void path_begin(const SceneView &sc, Path &p, Rng &rng, uint32_t x, uint32_t y, uint32_t s, uint32_t sqrt_n,
-                       uint32_t width, uint32_t height, uint64_t seed) {
-    uint64_t stream = ((uint64_t) y * width + x) * ((uint64_t) sqrt_n * sqrt_n) + s;
-    rng_seed(rng, seed, stream);
-    float sx, sy;
-    sample_offset(s, sqrt_n, &sx, &sy);
-    float u = fdiv(x + sx, (float) width);    // main.cpp:156-157
-    float v = fdiv(y + sy, (float) height);
-    p.ray = camera_get_ray(sc.cam, u, v, rng);
-    p.T = v3(1, 1, 1);
-    p.L = v3(0, 0, 0);
-    p.depth = 0;
 }
 
 }  // namespace mrt

@@ -84,13 +84,14 @@ int main(int argc, char **argv) {
                     Path p;
                     path_begin(sv, p, rng, x, y, s, sq, W, H, seed);
                     for (;;) {
+                        path_advance(sv, p);
                         cnt.rays++;
                         Hit rec;
                         Stack st;
                         st.base = stack_mem.data(); st.stride = 1; st.sp = 0;
                         bool hit = intersect(sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
                         if (st.sp != 0) { fprintf(stderr, "stack imbalance\n"); abort(); }
-                        if (!shade(sv, p, hit, rec, depth, rng)) break;
+                        if (!path_shade(sv, p, hit, rec, depth, rng)) break;
                     }
                     if (path_sample_finite(p)) {
                         color = color + p.L;
