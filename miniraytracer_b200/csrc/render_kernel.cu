@@ -157,6 +157,114 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
     }
 }
 
+// --------------------------------------------------------- mode W, phase-synchronised
+// Same stream logic per warp, but the warps of a (large) block run the three phases of an iteration
+// -- advance | intersect | shade -- between block barriers, so that the warps sharing an SM sub-partition
+// execute the same code region at the same time (instruction-cache reuse; ncu round 1: ~40 % of warp stalls
+// were stall_no_inst).  Warps take their tasks independently and keep attending the barriers until every
+// warp of the block has run out of work.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const RenderArgs a) {
+    extern __shared__ uint32_t smem_stack[];
+    constexpr uint32_t kWarps = THREADS / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Stack st;
+    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
+    st.stride = 32u;
+    st.sp = 0;
+    const uint32_t K = a.pixels_per_task;
+    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarps * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t ns = a.s_end - a.s_begin;
+    unsigned long long rays = 0, nonfinite = 0;
+
+    bool warp_done = false, have_task = false, alive = false;
+    uint32_t pix0 = 0, kp = 0, n_items = 0, next_i = 0, cur_k = 0xFFFFFFFFu;
+    Path p;
+    Rng rng;
+    float sr = 0, sg = 0, sb = 0, sc = 0;
+    for (;;) {
+        // ---- warp-level bookkeeping: top up dead lanes, switch chunks, retire
+        while (!warp_done) {
+            if (!have_task) {
+                uint32_t task = 0;
+                if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
+                task = __shfl_sync(0xFFFFFFFFu, task, 0);
+                if (task >= a.n_tasks) { warp_done = true; break; }
+                pix0 = task * K;
+                kp = min(K, n_pixels - pix0);
+                n_items = kp * ns;
+                for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                next_i = 0;
+                cur_k = 0xFFFFFFFFu;
+                sr = sg = sb = sc = 0;
+                have_task = true;
+            }
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !alive);
+            if (!alive) {
+                const uint32_t i = next_i + __popc(need & lt_mask);
+                if (i < n_items) {
+                    const uint32_t k = i / ns, s = a.s_begin + (i - k * ns);
+                    if (k != cur_k) {
+                        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
+                        sr = sg = sb = sc = 0;
+                        cur_k = k;
+                    }
+                    const uint32_t pix = pix0 + k;
+                    const uint32_t y = pix / a.width, x = pix - y * a.width;
+                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                    alive = true;
+                }
+            }
+            next_i = min(next_i + (uint32_t) __popc(need), n_items);
+            if (__any_sync(0xFFFFFFFFu, alive)) break;
+            // chunk finished: combine the lanes' partial sums, one writer per pixel
+            if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
+            __syncwarp();
+            for (uint32_t k = 0; k < kp; k++) {
+                float4 v = part[k * 32u];
+                v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                if (lane == 0) {
+                    const uint32_t pix = pix0 + k;
+                    if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    a.acc[pix] = v;
+                }
+            }
+            __syncwarp();
+            have_task = false;
+        }
+        if (__syncthreads_and(warp_done ? 1 : 0)) break;
+        // ---- phase B+C
+        if (alive) path_advance(a.sc, p);
+        __syncthreads();
+        // ---- phase D
+        Hit rec;
+        bool hit = false;
+        if (alive) {
+            rays++;
+            hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+        }
+        __syncthreads();
+        // ---- phase E
+        if (alive) {
+            if (!path_shade(a.sc, p, hit, rec, a.max_bounces, rng)) {
+                if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
+                else nonfinite++;
+                alive = false;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[2], nonfinite);
+    }
+}
+
 // ------------------------------------------------------------------ mode P
 template <int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const RenderArgs a) {
@@ -296,8 +404,9 @@ struct MrtScene {
     std::vector<void *> allocs;
     SceneView view;
     uint32_t stack_words = 0;
-    int min_blocks = 5;           // launch-bounds variant (MRT_MINB, tuning knob)
+    int min_blocks = 6;           // launch-bounds variant (MRT_MINB, tuning knob)
     uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
+    uint32_t sync_threads = 0;    // block size of the phase-synchronised variant (MRT_SYNC, 0 = off)
     cudaStream_t stream = nullptr;
     cudaStream_t poll_stream = nullptr;
     // accumulator
@@ -319,7 +428,7 @@ struct MrtScene {
     // last render
     bool rendered = false;
     MrtRenderParams last;
-    uint32_t last_tasks = 0, last_grid = 0, last_smem = 0, last_mode = 0;
+    uint32_t last_tasks = 0, last_grid = 0, last_block = kBlock, last_smem = 0, last_mode = 0;
     float4 *last_acc = nullptr;
 };
 
@@ -418,6 +527,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     s->stack_words = d->stack_words ? d->stack_words : 64;
     if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
     if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
+    if (const char *e = getenv("MRT_SYNC")) s->sync_threads = (uint32_t) atoi(e);
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -498,12 +608,22 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     int minb = s->min_blocks;
     typedef void (*kernel_t)(const RenderArgs);
     kernel_t kernel = nullptr;
-    switch (minb) {
-    case 4: kernel = mode_w ? render_pixel_per_warp<4> : render_pixel_per_lane<4>; break;
-    case 6: kernel = mode_w ? render_pixel_per_warp<6> : render_pixel_per_lane<6>; break;
-    case 8: kernel = mode_w ? render_pixel_per_warp<8> : render_pixel_per_lane<8>; break;
-    default: minb = 5; kernel = mode_w ? render_pixel_per_warp<5> : render_pixel_per_lane<5>; break;
+    uint32_t threads = kBlock;
+    if (mode_w && s->sync_threads) {   // experimental phase-synchronised variants (MRT_SYNC)
+        switch (s->sync_threads) {
+        case 256: threads = 256; kernel = (minb >= 3) ? render_stream_sync<256, 3> : render_stream_sync<256, 2>; break;
+        case 384: threads = 384; kernel = (minb >= 2) ? render_stream_sync<384, 2> : render_stream_sync<384, 1>; break;
+        default: threads = 512; kernel = render_stream_sync<512, 1>; break;
+        }
+    } else {
+        switch (minb) {
+        case 4: kernel = mode_w ? render_pixel_per_warp<4> : render_pixel_per_lane<4>; break;
+        case 6: kernel = mode_w ? render_pixel_per_warp<6> : render_pixel_per_lane<6>; break;
+        case 8: kernel = mode_w ? render_pixel_per_warp<8> : render_pixel_per_lane<8>; break;
+        default: minb = 5; kernel = mode_w ? render_pixel_per_warp<5> : render_pixel_per_lane<5>; break;
+        }
     }
+    const uint32_t warps_per_block = threads / 32u;
     // choose the task size so that every resident warp gets several tasks (load balance) while the idle
     // tail of a task stays small against its body
     uint32_t K = 1;
@@ -511,12 +631,12 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     int blocks_per_sm = 0;
     uint32_t resident_warps = 0;
     for (int pass = 0; pass < 2; pass++) {
-        smem = (size_t) kWarpsPerBlock * s->stack_words * 32u * sizeof(uint32_t);
-        if (mode_w) smem += (size_t) kWarpsPerBlock * K * 32u * sizeof(float4);
+        smem = (size_t) warps_per_block * s->stack_words * 32u * sizeof(uint32_t);
+        if (mode_w) smem += (size_t) warps_per_block * K * 32u * sizeof(float4);
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kBlock, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, (int) threads, smem));
         if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
-        resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * kWarpsPerBlock;
+        resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * warps_per_block;
         if (pass == 1) break;
         if (mode_w) {
             K = s->chunk_pixels ? s->chunk_pixels : 8u;
@@ -533,20 +653,21 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
     uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
-    const uint32_t blocks_needed = (a.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint32_t blocks_needed = (a.n_tasks + warps_per_block - 1) / warps_per_block;
     if (grid > blocks_needed) grid = blocks_needed;
 
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    kernel<<<grid, kBlock, smem, s->stream>>>(a);
+    kernel<<<grid, threads, smem, s->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     s->rendered = true;
     s->last = *p;
     s->last_tasks = a.n_tasks;
     s->last_grid = grid;
+    s->last_block = threads;
     s->last_smem = (uint32_t) smem;
     s->last_mode = mode_w ? 1u : 0u;
     s->last_acc = acc;
@@ -571,7 +692,7 @@ extern "C" int mrt_gpu_poll(MrtScene *s, float *pct_done, uint64_t *rays) {
     CUDA_TRY(cudaMemcpyAsync(&s->poll_host[1], &s->counters[0], sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->poll_stream));
     CUDA_TRY(cudaStreamSynchronize(s->poll_stream));
     // like work_queue_seq::getPercentDone (work_queue.cpp:142-149): tickets are taken at the start of work
-    double done = (double) (unsigned int) s->poll_host[0] - (double) s->last_grid * kWarpsPerBlock;
+    double done = (double) (unsigned int) s->poll_host[0] - (double) s->last_grid * (s->last_block / 32u);
     if (done < 0) done = 0;
     double pct = s->last_tasks ? done * 100.0 / s->last_tasks : 0.0;
     if (pct > 99.9) pct = 99.9;
@@ -601,7 +722,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     out->nonfinite = c[2];
     CUDA_TRY(cudaEventElapsedTime(&out->kernel_ms, s->ev0, s->ev1));
     out->grid = s->last_grid;
-    out->block = kBlock;
+    out->block = s->last_block;
     out->smem_bytes = s->last_smem;
     out->mode = s->last_mode;
     return MRT_OK;

@@ -11,11 +11,13 @@ from miniraytracer_b200 import api  # noqa: E402
 
 CASES = {
     "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
-    "C3": (6, 960, 540, 1024), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
+    "C3": (6, 960, 540, 1024), "P_C2": (5, 480, 270, 1024), "P_C1": (0, 256, 256, 1024), "P_C4": (7, 480, 270, 256),
+    "P_C5": (8, 480, 270, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
 }
 
 
 def measure(case, minb, chunk, reps=2):
+    reps = int(os.environ.get("MRT_SWEEP_REPS", reps))
     scene, w, h, spp = CASES[case]
     os.environ["MRT_MINB"] = str(minb)
     os.environ["MRT_CHUNK"] = str(chunk)
@@ -37,8 +39,13 @@ if __name__ == "__main__":
     ap.add_argument("--cases", default="C2")
     ap.add_argument("--minb", default="5")
     ap.add_argument("--chunk", default="0")
+    ap.add_argument("--sync", default="0")
     args = ap.parse_args()
     for case in args.cases.split(","):
         for minb in args.minb.split(","):
             for chunk in args.chunk.split(","):
-                print(json.dumps(measure(case, int(minb), int(chunk))), flush=True)
+                for sync in args.sync.split(","):
+                    os.environ["MRT_SYNC"] = sync
+                    res = measure(case, int(minb), int(chunk))
+                    res["sync"] = int(sync)
+                    print(json.dumps(res), flush=True)
