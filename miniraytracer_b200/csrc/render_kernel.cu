@@ -455,9 +455,16 @@ extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
         set_error("mrt_gpu_init: kernels are built for sm_100a only");
         return MRT_E_CUDA;
     }
-    if (info) {   // cudaGetDeviceProperties is slow (~100 ms): only on request
+    if (info) {   // cudaGetDeviceProperties is slow (~100 ms): only on request, cached per device
+        static cudaDeviceProp cached[64];
+        static bool have[64];
+        if (device < 64 && !have[device]) {
+            CUDA_TRY(cudaGetDeviceProperties(&cached[device], device));
+            have[device] = true;
+        }
         cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (device < 64) prop = cached[device];
+        else CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         memset(info, 0, sizeof(*info));
         info->device = device;
         info->sm_count = prop.multiProcessorCount;
