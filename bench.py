@@ -132,8 +132,8 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------------ our arm
 def scene_bytes(desc):
     d = desc.contents
-    return 16 * (3 * d.n_sphere + 2 * d.n_rect + 2 * d.n_list + 2 * d.n_bvh + 2 * d.n_pod + 6 * d.n_tri + d.n_xlate + 3 * d.n_rot +
-                 d.n_vol + d.n_mat + d.n_tex + (256 if d.perlin_vec else 0)) + 4 * (d.n_child + d.n_lights + (768 if d.perlin_perm else 0)) + \
+    return 16 * (3 * d.n_sphere + 2 * d.n_rect + 2 * d.n_list + 2 * d.n_bvh + 4 * d.n_node2 + 6 * d.n_tri + d.n_xlate + 3 * d.n_rot +
+                 d.n_vol + d.n_mat + d.n_tex + (256 if d.perlin_vec else 0)) + 4 * (d.n_child + d.n_lights + 2 * d.n_trileaf + (768 if d.perlin_perm else 0)) + \
         int(d.n_image_bytes)
 
 

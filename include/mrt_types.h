@@ -17,11 +17,21 @@
 //   list[2*i+0]   = (box.min.xyz, bits(first_child))            scene_object.h:37-44
 //   list[2*i+1]   = (box.max.xyz, bits(count | hasBox<<31))
 //                   children = child[first_child .. +count], then MRT_REF_END
-//   bvh[2*i+0]    = (box.min.xyz, bits(left  | (order & 15) << 28))   scene_object.h:138-144
-//   bvh[2*i+1]    = (box.max.xyz, bits(right | (order >> 4) << 28))
-//   pod[2*i+0]    = (box.min.xyz, bits(left or first triangle))       triangle.h:46-56
-//   pod[2*i+1]    = (box.max.xyz, bits(prim_count | order << 16))  prim_count==0: inner
-//                   (left / first triangle are absolute indices into pod[] / tri[])
+//   Both of the reference's BVHs -- bvh_node<T> (scene_object.h:138-244) and pod_bvh<triangle>
+//   (triangle.h:46-213) -- have the same traversal rule (test the node's own box; visit the closer child
+//   by node_order & dirMask; return on its first hit; else the farther child; tmin/tmax never change
+//   inside one tree).  They are flattened into ONE node format in which a node carries its CHILDREN's
+//   boxes, so one visit decides both children (the box test is a pure function of the ray and the
+//   unchanged tmin/tmax, so testing a child's box at its parent gives the same answer):
+//   bvh[2*i+0]    = (root box.min.xyz, bits(root child ref))        root header: the tree's own box test
+//   bvh[2*i+1]    = (root box.max.xyz, 0)
+//   node2[4*i+0]  = (left  box.min.xyz, bits(left ref  | (order & 15) << 28))
+//   node2[4*i+1]  = (left  box.max.xyz, bits(right ref | (order >> 4) << 28))
+//   node2[4*i+2]  = (right box.min.xyz, bits(flags))  flags bit0/bit1: left/right child has a box to test
+//   node2[4*i+3]  = (right box.max.xyz, 0)
+//                   child refs: NODE2 (inner), LIST (header copy with hasBox = 0: its box is the one stored
+//                   here), TRILEAF, or any other object (no box flag -> visited unconditionally)
+//   trileaf[2*i]  = first triangle, trileaf[2*i+1] = triangle count      (pod_bvh leaf, triangle.h:179-187)
 //   tri[3*i+0..2] = (m.xyz, bits(mat)), (u.xyz, 0), (v.xyz, 0)         triangle.h:13-22
 //   trin[3*i+0..2]= (mn.xyz,0), (un.xyz,0), (vn.xyz,0)
 //   xlate[i]      = (offset.xyz, bits(child))                          scene_object.h:325-333
@@ -57,10 +67,11 @@ enum MrtRefType {
     MRT_T_RECT_YZ = 3,
     MRT_T_LIST = 4,
     MRT_T_BVH = 5,
-    MRT_T_POD = 6,
+    MRT_T_NODE2 = 6,
     MRT_T_TRANSLATE = 7,
     MRT_T_ROTATE_Y = 8,
     MRT_T_VOLUME = 9,
+    MRT_T_TRILEAF = 10,
     MRT_T_END = 15 /* list terminator */
 };
 #define MRT_REF(type, index) ((uint32_t) (((uint32_t) (type) << 24) | ((uint32_t) (index) & 0xFFFFFFu)))
@@ -106,7 +117,8 @@ typedef struct MrtSceneDesc {
     const MrtF4 *list;    uint32_t n_list;
     const uint32_t *child; uint32_t n_child;
     const MrtF4 *bvh;     uint32_t n_bvh;
-    const MrtF4 *pod;     uint32_t n_pod;
+    const MrtF4 *node2;   uint32_t n_node2;
+    const uint32_t *trileaf; uint32_t n_trileaf;
     const MrtF4 *tri;     uint32_t n_tri;
     const MrtF4 *trin;
     const MrtF4 *xlate;   uint32_t n_xlate;

@@ -30,7 +30,8 @@ class SceneDesc(C.Structure):
         ("list", C.POINTER(F4)), ("n_list", C.c_uint32),
         ("child", C.POINTER(C.c_uint32)), ("n_child", C.c_uint32),
         ("bvh", C.POINTER(F4)), ("n_bvh", C.c_uint32),
-        ("pod", C.POINTER(F4)), ("n_pod", C.c_uint32),
+        ("node2", C.POINTER(F4)), ("n_node2", C.c_uint32),
+        ("trileaf", C.POINTER(C.c_uint32)), ("n_trileaf", C.c_uint32),
         ("tri", C.POINTER(F4)), ("n_tri", C.c_uint32),
         ("trin", C.POINTER(F4)),
         ("xlate", C.POINTER(F4)), ("n_xlate", C.c_uint32),

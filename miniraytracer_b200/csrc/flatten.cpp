@@ -108,6 +108,66 @@ struct Flattener {
         return k == NodeKind::Sphere || k == NodeKind::RectXY || k == NodeKind::RectXZ || k == NodeKind::RectYZ;
     }
 
+    // ---- wide BVH nodes (children's boxes stored in the parent, see mrt_types.h)
+    std::map<int, uint32_t> list_nobox_memo;
+    uint32_t list_nobox(int id) {   // header copy with hasBox = 0 sharing the child table of the original list
+        auto it = list_nobox_memo.find(id);
+        if (it != list_nobox_memo.end()) return it->second;
+        uint32_t orig = node(id);
+        uint32_t oi = MRT_REF_INDEX(orig);
+        MrtF4 h0 = o.list[2 * oi], h1 = o.list[2 * oi + 1];
+        uint32_t w1; memcpy(&w1, &h1.w, 4);
+        uint32_t i = (uint32_t) o.list.size() / 2;
+        o.list.push_back(h0);
+        o.list.push_back(f4(h1.x, h1.y, h1.z, ubits(w1 & 0x7FFFFFFFu)));
+        uint32_t r = MRT_REF(MRT_T_LIST, i);
+        list_nobox_memo[id] = r;
+        return r;
+    }
+    // child of a bvh_node: the ref to visit once the child's own box (if it has one) has been passed
+    uint32_t bvh_child(int id, Aabb *box, bool *has_box) {
+        const Node &c = g.nodes[id];
+        switch (c.kind) {
+        case NodeKind::Bvh: *box = c.box; *has_box = true; return bvh_inner(id);
+        case NodeKind::List: *box = c.box; *has_box = c.has_box; return c.has_box ? list_nobox(id) : node(id);
+        case NodeKind::Box: return bvh_child(c.child, box, has_box);   // box::hit == its rect list's hit (box.h:23-25)
+        default: *has_box = false; *box = Aabb(); return wrap(node(id));   // spheres, transforms, ...: no box test of their own here
+        }
+    }
+    void push_node2(const Aabb &lb, bool lhas, uint32_t l, const Aabb &rb, bool rhas, uint32_t r, uint8_t order) {
+        o.node2.push_back(f4(lb.min.x, lb.min.y, lb.min.z, ubits(l | ((uint32_t) (order & 15u) << 28))));
+        o.node2.push_back(f4(lb.max.x, lb.max.y, lb.max.z, ubits(r | ((uint32_t) (order >> 4) << 28))));
+        o.node2.push_back(f4(rb.min.x, rb.min.y, rb.min.z, ubits((lhas ? 1u : 0u) | (rhas ? 2u : 0u))));
+        o.node2.push_back(f4(rb.max.x, rb.max.y, rb.max.z, 0));
+    }
+    std::map<int, uint32_t> inner_memo;
+    uint32_t bvh_inner(int id) {
+        auto it = inner_memo.find(id);
+        if (it != inner_memo.end()) return it->second;
+        const Node &n = g.nodes[id];
+        Aabb lb, rb;
+        bool lhas = false, rhas = false;
+        uint32_t l = bvh_child(n.left, &lb, &lhas), r = bvh_child(n.right, &rb, &rhas);
+        uint32_t i = (uint32_t) o.node2.size() / 4;
+        push_node2(lb, lhas, l, rb, rhas, r, n.order);
+        uint32_t ref = MRT_REF(MRT_T_NODE2, i);
+        inner_memo[id] = ref;
+        return ref;
+    }
+    uint32_t pod_child(const Mesh &mesh, uint32_t ni, uint32_t tri_base) {
+        const PodNode &pn = mesh.nodes[ni];
+        if (pn.prim_count) {
+            uint32_t i = (uint32_t) o.trileaf.size() / 2;
+            o.trileaf.push_back(tri_base + pn.prim_offset);
+            o.trileaf.push_back(pn.prim_count);
+            return MRT_REF(MRT_T_TRILEAF, i);
+        }
+        uint32_t l = pod_child(mesh, pn.left, tri_base), r = pod_child(mesh, pn.left + 1, tri_base);
+        uint32_t i = (uint32_t) o.node2.size() / 4;
+        push_node2(mesh.nodes[pn.left].box, true, l, mesh.nodes[pn.left + 1].box, true, r, pn.order);
+        return MRT_REF(MRT_T_NODE2, i);
+    }
+
     uint32_t node(int id) {
         auto it = memo.find(id);
         if (it != memo.end()) return it->second;
@@ -151,11 +211,11 @@ struct Flattener {
             ref = MRT_REF(MRT_T_LIST, i);
             break;
         }
-        case NodeKind::Bvh: {
-            uint32_t l = wrap(node(n.left)), r = wrap(node(n.right));
+        case NodeKind::Bvh: {   // root header: the tree's own box test, then the wide nodes
+            uint32_t root = bvh_inner(id);
             uint32_t i = (uint32_t) o.bvh.size() / 2;
-            o.bvh.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(l | ((uint32_t) (n.order & 15u) << 28))));
-            o.bvh.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, ubits(r | ((uint32_t) (n.order >> 4) << 28))));
+            o.bvh.push_back(f4(n.box.min.x, n.box.min.y, n.box.min.z, ubits(root)));
+            o.bvh.push_back(f4(n.box.max.x, n.box.max.y, n.box.max.z, 0));
             ref = MRT_REF(MRT_T_BVH, i);
             break;
         }
@@ -187,15 +247,7 @@ struct Flattener {
         case NodeKind::PodBvh: {
             const Mesh &mesh = g.meshes[n.mesh];
             uint32_t m = mat(mesh.mat);
-            uint32_t node_base = (uint32_t) o.pod.size() / 2;
             uint32_t tri_base = (uint32_t) o.tri.size() / 3;
-            for (const PodNode &pn : mesh.nodes) {
-                if (pn.prim_count > 0xFFFFu) fail("pod_bvh leaf with more than 65535 triangles");
-                uint32_t w0 = pn.prim_count ? tri_base + pn.prim_offset : node_base + pn.left;
-                uint32_t w1 = pn.prim_count ? pn.prim_count : ((uint32_t) pn.order << 16);
-                o.pod.push_back(f4(pn.box.min.x, pn.box.min.y, pn.box.min.z, ubits(w0)));
-                o.pod.push_back(f4(pn.box.max.x, pn.box.max.y, pn.box.max.z, ubits(w1)));
-            }
             for (const Triangle &t : mesh.tris) {
                 o.tri.push_back(f4(t.m.x, t.m.y, t.m.z, ubits(m)));
                 o.tri.push_back(f4(t.u.x, t.u.y, t.u.z, 0));
@@ -204,7 +256,12 @@ struct Flattener {
                 o.trin.push_back(f4(t.un.x, t.un.y, t.un.z, 0));
                 o.trin.push_back(f4(t.vn.x, t.vn.y, t.vn.z, 0));
             }
-            ref = MRT_REF(MRT_T_POD, node_base);
+            uint32_t root = pod_child(mesh, 0, tri_base);
+            uint32_t i = (uint32_t) o.bvh.size() / 2;
+            const Aabb &rb = mesh.nodes[0].box;
+            o.bvh.push_back(f4(rb.min.x, rb.min.y, rb.min.z, ubits(root)));
+            o.bvh.push_back(f4(rb.max.x, rb.max.y, rb.max.z, 0));
+            ref = MRT_REF(MRT_T_BVH, i);
             break;
         }
         }
@@ -262,7 +319,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     }
     const size_t lim = 0xFFFFFFu;
     if (o.sphere.size() / 3 > lim || o.rect.size() / 2 > lim || o.list.size() / 2 > lim || o.bvh.size() / 2 > lim ||
-        o.pod.size() / 2 > lim || o.xlate.size() > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
+        o.node2.size() / 4 > lim || o.trileaf.size() / 2 > lim || o.xlate.size() > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
         fl.fail("too many objects of one type for a 24-bit index");
     if (o.child.size() > 0x0FFFFFFFu) fl.fail("child table too large");
     if (!fl.ok) return false;
@@ -284,7 +341,8 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     d.list = o.list.data();     d.n_list = (uint32_t) o.list.size() / 2;
     d.child = o.child.data();   d.n_child = (uint32_t) o.child.size();
     d.bvh = o.bvh.data();       d.n_bvh = (uint32_t) o.bvh.size() / 2;
-    d.pod = o.pod.data();       d.n_pod = (uint32_t) o.pod.size() / 2;
+    d.node2 = o.node2.data();   d.n_node2 = (uint32_t) o.node2.size() / 4;
+    d.trileaf = o.trileaf.data(); d.n_trileaf = (uint32_t) o.trileaf.size() / 2;
     d.tri = o.tri.data();       d.n_tri = (uint32_t) o.tri.size() / 3;
     d.trin = o.trin.data();
     d.xlate = o.xlate.data();   d.n_xlate = (uint32_t) o.xlate.size();

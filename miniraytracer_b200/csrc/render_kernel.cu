@@ -515,7 +515,8 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if ((rc = upload(s, d->list, (size_t) d->n_list * 2, &v.list))) return fail(rc);
     if ((rc = upload(s, d->child, (size_t) d->n_child, &v.child))) return fail(rc);
     if ((rc = upload(s, d->bvh, (size_t) d->n_bvh * 2, &v.bvh))) return fail(rc);
-    if ((rc = upload(s, d->pod, (size_t) d->n_pod * 2, &v.pod))) return fail(rc);
+    if ((rc = upload(s, d->node2, (size_t) d->n_node2 * 4, &v.node2))) return fail(rc);
+    if ((rc = upload(s, d->trileaf, (size_t) d->n_trileaf * 2, &v.trileaf))) return fail(rc);
     if ((rc = upload(s, d->tri, (size_t) d->n_tri * 3, &v.tri))) return fail(rc);
     if ((rc = upload(s, d->trin, (size_t) d->n_tri * 3, &v.trin))) return fail(rc);
     if ((rc = upload(s, d->xlate, (size_t) d->n_xlate, &v.xlate))) return fail(rc);

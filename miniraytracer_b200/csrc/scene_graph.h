@@ -178,8 +178,8 @@ void dump_scene(const SceneGraph &g, FILE *f);
 
 // flattener: graph -> mrt_types.h tables
 struct FlatScene {
-    std::vector<MrtF4> sphere, rect, list, bvh, pod, tri, trin, xlate, rot, vol, mat, tex, perlin_vec;
-    std::vector<uint32_t> child, lights;
+    std::vector<MrtF4> sphere, rect, list, bvh, node2, tri, trin, xlate, rot, vol, mat, tex, perlin_vec;
+    std::vector<uint32_t> child, lights, trileaf;
     std::vector<int32_t> perlin_perm;
     std::vector<uint8_t> image;
     MrtSceneDesc desc;

@@ -216,8 +216,8 @@ MRT_HD bool aabb_hit(const MrtF4 &bmin, const MrtF4 &bmax, const Ray &r, float t
 
 // -------------------------------------------------------------- scene (device)
 struct SceneView {
-    const MrtF4 *sphere, *rect, *list, *bvh, *pod, *tri, *trin, *xlate, *rot, *vol, *mat, *tex, *perlin_vec;
-    const uint32_t *child, *lights;
+    const MrtF4 *sphere, *rect, *list, *bvh, *node2, *tri, *trin, *xlate, *rot, *vol, *mat, *tex, *perlin_vec;
+    const uint32_t *child, *lights, *trileaf;
     const int32_t *perlin_perm;
     const uint8_t *image;
     uint32_t root, n_lights, sky;
@@ -405,43 +405,58 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 st.push(MRT_FRAME(MRT_F_LIST, f2u(l0.w)));
                 break;   // the LIST frame is popped right away and runs the child loop
             }
-            case MRT_T_BVH: {
+            case MRT_T_BVH: {   // root of a bvh_node / pod_bvh tree: its own box test (scene_object.h:211, triangle.h:175)
                 MrtF4 b0 = ld4(sc.bvh, 2 * idx), b1 = ld4(sc.bvh, 2 * idx + 1);
                 if (cnt) cnt->aabb++;
                 ret = false;
                 if (!aabb_hit(b0, b1, ray, tmin, tmax)) break;
-                uint32_t w0 = f2u(b0.w), w1 = f2u(b1.w);
-                uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
-                uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
-                bool lfirst = (order & ray.mask) != 0;
-                st.push(MRT_FRAME(MRT_F_IF_MISS, lfirst ? right : left));
-                cur = lfirst ? left : right;
+                cur = f2u(b0.w);
                 descend = true;
                 break;
             }
-            case MRT_T_POD: {
-                MrtF4 p0 = ld4(sc.pod, 2 * idx), p1 = ld4(sc.pod, 2 * idx + 1);
-                if (cnt) cnt->aabb++;
+            case MRT_T_NODE2: {
+                // Inner node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
+                // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
+                // (IF_MISS frame).  tmin/tmax are constant inside a tree, so the child box tests made here are
+                // the ones the children would make on entry.
                 ret = false;
-                if (!aabb_hit(p0, p1, ray, tmin, tmax)) break;
-                uint32_t w1 = f2u(p1.w);
-                uint32_t count = w1 & 0xFFFFu;
-                if (count) {   // leaf: closest hit among its triangles (triangle.h:179-187)
-                    uint32_t first = f2u(p0.w);
-                    for (uint32_t i = 0; i < count; i++) {
-                        if (cnt) cnt->tri++;
-                        if (hit_triangle(sc, first + i, ray, tmin, tmax, !probe, rec)) {
-                            ret = true;
-                            tmax = rec.t;
-                        }
+                for (;;) {
+                    const uint32_t ni = MRT_REF_INDEX(cur);
+                    MrtF4 n0 = ld4(sc.node2, 4 * ni), n1 = ld4(sc.node2, 4 * ni + 1);
+                    MrtF4 n2 = ld4(sc.node2, 4 * ni + 2), n3 = ld4(sc.node2, 4 * ni + 3);
+                    const uint32_t w0 = f2u(n0.w), w1 = f2u(n1.w), flags = f2u(n2.w);
+                    const uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
+                    const uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
+                    const bool hl = !(flags & 1u) || aabb_hit(n0, n1, ray, tmin, tmax);
+                    const bool hr = !(flags & 2u) || aabb_hit(n2, n3, ray, tmin, tmax);
+                    const bool lfirst = (order & ray.mask) != 0;
+                    const bool h_first = lfirst ? hl : hr, h_second = lfirst ? hr : hl;
+                    const uint32_t first = lfirst ? left : right, second = lfirst ? right : left;
+                    if (cnt) cnt->aabb += ((lfirst ? flags : flags >> 1) & 1u);   // the closer child's own test
+                    if (h_first) {
+                        if (h_second) st.push(MRT_FRAME(MRT_F_IF_MISS, second));
+                        else if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);   // farther child would be entered and miss its box
+                        cur = first;
+                    } else if (h_second) {
+                        if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);
+                        cur = second;
+                    } else {
+                        if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);
+                        break;
                     }
-                } else {
-                    uint32_t order = (w1 >> 16) & 0xFFu;
-                    uint32_t left = f2u(p0.w);
-                    bool lfirst = (order & ray.mask) != 0;
-                    st.push(MRT_FRAME(MRT_F_IF_MISS, MRT_REF(MRT_T_POD, lfirst ? left + 1 : left)));
-                    cur = MRT_REF(MRT_T_POD, lfirst ? left : left + 1);
-                    descend = true;
+                    if (MRT_REF_TYPE(cur) != MRT_T_NODE2) { descend = true; break; }
+                }
+                break;
+            }
+            case MRT_T_TRILEAF: {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
+                const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
+                ret = false;
+                for (uint32_t i = 0; i < count; i++) {
+                    if (cnt) cnt->tri++;
+                    if (hit_triangle(sc, first + i, ray, tmin, tmax, !probe, rec)) {
+                        ret = true;
+                        tmax = rec.t;
+                    }
                 }
                 break;
             }

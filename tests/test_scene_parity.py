@@ -55,7 +55,7 @@ def test_flat_scene_shapes():
     hs.close()
     hs = api.HostScene(0, 500, 500)
     d = hs.desc.contents
-    assert d.sky == 1 and d.n_lights == 0 and d.n_sphere > 400 and d.n_bvh > 50
+    assert d.sky == 1 and d.n_lights == 0 and d.n_sphere > 400 and d.n_bvh == 1 and d.n_node2 > 50
     hs.close()
 
 
