@@ -58,10 +58,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One segment of a live path: traverse, shade.  Returns true while the path continues.
-__device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng, Stack &st) {
+// Called by ALL lanes of the warp (the traversal loop votes); lanes without a live path pass alive = false.
+__device__ __forceinline__ bool path_step(const RenderArgs &a, bool alive, Path &p, Rng &rng, Stack &st) {
     Hit rec;
-    path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
-    bool hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+    if (alive) path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
+    bool hit = intersect(a.sc, alive, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+    if (!alive) return false;
     return path_shade(a.sc, p, hit, rec, a.max_bounces, rng);
 }
 
@@ -124,9 +126,10 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
             }
             next_i = min(next_i + (uint32_t) __popc(need), n_items);
             if (!__any_sync(0xFFFFFFFFu, alive)) break;
+            const bool cont = path_step(a, alive, p, rng, st);
             if (alive) {
                 rays++;
-                if (!path_step(a, p, rng, st)) {
+                if (!cont) {
                     if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
                     else nonfinite++;
                     alive = false;
@@ -240,11 +243,8 @@ __global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const Render
         __syncthreads();
         // ---- phase D
         Hit rec;
-        bool hit = false;
-        if (alive) {
-            rays++;
-            hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
-        }
+        if (alive) rays++;
+        bool hit = intersect(a.sc, alive, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
         __syncthreads();
         // ---- phase E
         if (alive) {
@@ -305,13 +305,14 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
             }
             next_p = min(next_p + (uint32_t) __popc(need), end_p);
             if (!__any_sync(0xFFFFFFFFu, has_pixel)) break;
+            if (has_pixel && !alive) {
+                path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                alive = true;
+            }
+            const bool cont = path_step(a, alive, p, rng, st);
             if (has_pixel) {
-                if (!alive) {
-                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
-                    alive = true;
-                }
                 rays++;
-                if (!path_step(a, p, rng, st)) {
+                if (!cont) {
                     if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
                     else nonfinite++;
                     alive = false;

@@ -12,7 +12,7 @@ from miniraytracer_b200 import api  # noqa: E402
 CASES = {
     "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
     "C3": (6, 960, 540, 1024), "P_C2": (5, 480, 270, 1024), "P_C1": (0, 256, 256, 1024), "P_C4": (7, 480, 270, 256),
-    "P_C5": (8, 480, 270, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
+    "P_C5": (8, 480, 270, 256), "Q_C4": (7, 320, 180, 256), "Q_C5": (8, 320, 180, 256), "Q_C1": (0, 200, 200, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
 }
 
 
