@@ -109,6 +109,7 @@ typedef struct MrtRenderStats {
     uint64_t rays;       /* trace() calls = path segments (G_rayCounter, main.cpp:68) */
     uint64_t paths;      /* (pixel, sample) pairs */
     uint64_t nonfinite;  /* samples dropped by the finite check (main.cpp:163-165) */
+    uint64_t warp_iterations; /* segment steps executed per warp, summed: rays / (32 * this) = share of lanes with a live path */
     float kernel_ms;     /* CUDA-event time of the render kernel on its stream */
     uint32_t grid, block, smem_bytes, mode;
 } MrtRenderStats;

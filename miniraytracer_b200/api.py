@@ -65,7 +65,7 @@ class DeviceInfo(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("nonfinite", C.c_uint64), ("kernel_ms", C.c_float),
+    _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("nonfinite", C.c_uint64), ("warp_iterations", C.c_uint64), ("kernel_ms", C.c_float),
                 ("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32), ("mode", C.c_uint32)]
 
 

@@ -58,12 +58,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One segment of a live path: traverse, shade.  Returns true while the path continues.
-// Called by ALL lanes of the warp (the traversal loop votes); lanes without a live path pass alive = false.
-__device__ __forceinline__ bool path_step(const RenderArgs &a, bool alive, Path &p, Rng &rng, Stack &st) {
+__device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng, Stack &st) {
     Hit rec;
-    if (alive) path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
-    bool hit = intersect(a.sc, alive, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
-    if (!alive) return false;
+    path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
+    bool hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
     return path_shade(a.sc, p, hit, rec, a.max_bounces, rng);
 }
 
@@ -88,7 +86,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_pixels = a.width * a.height;
     const uint32_t ns = a.s_end - a.s_begin;
-    unsigned long long rays = 0, nonfinite = 0;
+    unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
     for (;;) {
         uint32_t task = 0;
@@ -126,10 +124,10 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
             }
             next_i = min(next_i + (uint32_t) __popc(need), n_items);
             if (!__any_sync(0xFFFFFFFFu, alive)) break;
-            const bool cont = path_step(a, alive, p, rng, st);
+            iters++;
             if (alive) {
                 rays++;
-                if (!cont) {
+                if (!path_step(a, p, rng, st)) {
                     if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
                     else nonfinite++;
                     alive = false;
@@ -156,6 +154,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
     }
     if (lane == 0) {
         atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
         atomicAdd(&a.counters[2], nonfinite);
     }
 }
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const Render
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_pixels = a.width * a.height;
     const uint32_t ns = a.s_end - a.s_begin;
-    unsigned long long rays = 0, nonfinite = 0;
+    unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
     bool warp_done = false, have_task = false, alive = false;
     uint32_t pix0 = 0, kp = 0, n_items = 0, next_i = 0, cur_k = 0xFFFFFFFFu;
@@ -238,13 +237,17 @@ __global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const Render
             have_task = false;
         }
         if (__syncthreads_and(warp_done ? 1 : 0)) break;
+        if (!warp_done) iters++;
         // ---- phase B+C
         if (alive) path_advance(a.sc, p);
         __syncthreads();
         // ---- phase D
         Hit rec;
-        if (alive) rays++;
-        bool hit = intersect(a.sc, alive, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+        bool hit = false;
+        if (alive) {
+            rays++;
+            hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
+        }
         __syncthreads();
         // ---- phase E
         if (alive) {
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const Render
     }
     if (lane == 0) {
         atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
         atomicAdd(&a.counters[2], nonfinite);
     }
 }
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
     st.sp = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_pixels = a.width * a.height;
-    unsigned long long rays = 0, nonfinite = 0;
+    unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
     for (;;) {
         uint32_t task = 0;
@@ -305,14 +309,14 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
             }
             next_p = min(next_p + (uint32_t) __popc(need), end_p);
             if (!__any_sync(0xFFFFFFFFu, has_pixel)) break;
-            if (has_pixel && !alive) {
-                path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
-                alive = true;
-            }
-            const bool cont = path_step(a, alive, p, rng, st);
+            iters++;
             if (has_pixel) {
+                if (!alive) {
+                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                    alive = true;
+                }
                 rays++;
-                if (!cont) {
+                if (!path_step(a, p, rng, st)) {
                     if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
                     else nonfinite++;
                     alive = false;
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
     }
     if (lane == 0) {
         atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
         atomicAdd(&a.counters[2], nonfinite);
     }
 }
@@ -729,6 +734,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     out->rays = c[0];
     out->paths = (uint64_t) s->last.width * s->last.height * (s->last.sample_end - s->last.sample_begin);
     out->nonfinite = c[2];
+    out->warp_iterations = c[1];
     CUDA_TRY(cudaEventElapsedTime(&out->kernel_ms, s->ev0, s->ev1));
     out->grid = s->last_grid;
     out->block = s->last_block;

@@ -378,100 +378,79 @@ MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float 
 //    (tmin, tmax) and only needs the two distances -> `probe` mode, in which
 //    hits update tmax only and the main record is untouched.  A volume's
 //    boundary must not contain another volume (checked by the flattener).
-//
-// Control flow is ONE warp-synchronous loop (the vote at its head makes all lanes reconverge every
-// iteration); per iteration a lane performs one action selected by its state:
-//   cur is a NODE2 ref      -> the tight inner-node loop (box tests, IF_MISS push/pop) until it leaves the tree
-//   cur is another ref      -> visit it (list header, tree root, triangle leaf, transform, volume)
-//   cur == NONE (returning) -> pop one frame and act on it (list continuation incl. the inline primitive
-//                              loop, transform restore, volume phases)
-// Lanes in the same state execute together whatever path led them there (ncu round 1: 14-23 % warp execution
-// efficiency in the BVH scenes when lanes were left to drift through nested loops).
-// `valid` = false lanes take no action but keep voting.
-#ifdef __CUDA_ARCH__
-#define MRT_WARP_ANY(pred) __any_sync(0xFFFFFFFFu, (pred))
-#else
-#define MRT_WARP_ANY(pred) (pred)
-#endif
-#define MRT_CUR_NONE 0xFFFFFFFFu
-
-MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
+MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
                       Counters *cnt) {
     float tmin = tmin0, tmax = tmax0;
     float main_tmax = tmax0;
     bool probe = false;
     float vol_t1 = 0.0f;
-    uint32_t cur = valid ? sc.root : MRT_CUR_NONE;
+    uint32_t cur = sc.root;
     bool ret = false;
     const uint32_t sp0 = st.sp;
 
     for (;;) {
-        const bool active = (cur != MRT_CUR_NONE) || (st.sp != sp0);
-        if (!MRT_WARP_ANY(active)) break;
-        if (!active) continue;
-
-        if (cur != MRT_CUR_NONE && MRT_REF_TYPE(cur) == MRT_T_NODE2) {
-            // ---------------------------------------------------------- inner nodes
-            // Node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
-            // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
-            // (IF_MISS frame).  tmin/tmax are constant inside a tree, so the child box tests made here are
-            // the ones the children would make on entry.
-            do {
-                const uint32_t ni = MRT_REF_INDEX(cur);
-                MrtF4 n0 = ld4(sc.node2, 4 * ni), n1 = ld4(sc.node2, 4 * ni + 1);
-                MrtF4 n2 = ld4(sc.node2, 4 * ni + 2), n3 = ld4(sc.node2, 4 * ni + 3);
-                const uint32_t w0 = f2u(n0.w), w1 = f2u(n1.w), flags = f2u(n2.w);
-                const uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
-                const uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
-                const bool hl = !(flags & 1u) || aabb_hit(n0, n1, ray, tmin, tmax);
-                const bool hr = !(flags & 2u) || aabb_hit(n2, n3, ray, tmin, tmax);
-                const bool lfirst = (order & ray.mask) != 0;
-                const bool h_first = lfirst ? hl : hr, h_second = lfirst ? hr : hl;
-                const uint32_t first = lfirst ? left : right, second = lfirst ? right : left;
-                if (cnt) cnt->aabb += (flags & 1u) + ((flags >> 1) & 1u);
-                if (h_first) {
-                    if (h_second) st.push(MRT_FRAME(MRT_F_IF_MISS, second));
-                    cur = first;
-                } else if (h_second) {
-                    cur = second;
-                } else {
-                    // both children missed: this subtree reports no hit; resume with the nearest pending
-                    // farther child, if the frame on top of the stack is one
-                    ret = false;
-                    cur = MRT_CUR_NONE;
-                    if (st.sp != sp0) {
-                        const uint32_t e = st.base[(st.sp - 1) * st.stride];
-                        if ((e >> 29) == MRT_F_IF_MISS) { st.sp--; cur = e & 0x0FFFFFFFu; }
-                    }
-                }
-            } while (cur != MRT_CUR_NONE && MRT_REF_TYPE(cur) == MRT_T_NODE2);
-            continue;
-        }
-
-        if (cur != MRT_CUR_NONE) {
-            // ------------------------------------------------------------- visit
+        // ------------------------------------------------------------ visit
+        bool descend = true;
+        while (descend) {
+            descend = false;
             const uint32_t type = MRT_REF_TYPE(cur), idx = MRT_REF_INDEX(cur);
-            ret = false;
-            uint32_t next = MRT_CUR_NONE;
             switch (type) {
-            case MRT_T_LIST: {   // object_list: own box test, then the child loop (LIST frame)
+            case MRT_T_LIST: {
                 MrtF4 l0 = ld4(sc.list, 2 * idx), l1 = ld4(sc.list, 2 * idx + 1);
+                ret = false;
                 if (f2u(l1.w) >> 31) {
                     if (cnt) cnt->aabb++;
                     if (!aabb_hit(l0, l1, ray, tmin, tmax)) break;
                 }
                 st.push(MRT_FRAME(MRT_F_LIST, f2u(l0.w)));
-                break;
+                break;   // the LIST frame is popped right away and runs the child loop
             }
             case MRT_T_BVH: {   // root of a bvh_node / pod_bvh tree: its own box test (scene_object.h:211, triangle.h:175)
                 MrtF4 b0 = ld4(sc.bvh, 2 * idx), b1 = ld4(sc.bvh, 2 * idx + 1);
                 if (cnt) cnt->aabb++;
+                ret = false;
                 if (!aabb_hit(b0, b1, ray, tmin, tmax)) break;
-                next = f2u(b0.w);
+                cur = f2u(b0.w);
+                descend = true;
+                break;
+            }
+            case MRT_T_NODE2: {
+                // Inner node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
+                // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
+                // (IF_MISS frame).  tmin/tmax are constant inside a tree, so the child box tests made here are
+                // the ones the children would make on entry.
+                ret = false;
+                for (;;) {
+                    const uint32_t ni = MRT_REF_INDEX(cur);
+                    MrtF4 n0 = ld4(sc.node2, 4 * ni), n1 = ld4(sc.node2, 4 * ni + 1);
+                    MrtF4 n2 = ld4(sc.node2, 4 * ni + 2), n3 = ld4(sc.node2, 4 * ni + 3);
+                    const uint32_t w0 = f2u(n0.w), w1 = f2u(n1.w), flags = f2u(n2.w);
+                    const uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
+                    const uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
+                    const bool hl = !(flags & 1u) || aabb_hit(n0, n1, ray, tmin, tmax);
+                    const bool hr = !(flags & 2u) || aabb_hit(n2, n3, ray, tmin, tmax);
+                    const bool lfirst = (order & ray.mask) != 0;
+                    const bool h_first = lfirst ? hl : hr, h_second = lfirst ? hr : hl;
+                    const uint32_t first = lfirst ? left : right, second = lfirst ? right : left;
+                    if (cnt) cnt->aabb += ((lfirst ? flags : flags >> 1) & 1u);   // the closer child's own test
+                    if (h_first) {
+                        if (h_second) st.push(MRT_FRAME(MRT_F_IF_MISS, second));
+                        else if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);   // farther child would be entered and miss its box
+                        cur = first;
+                    } else if (h_second) {
+                        if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);
+                        cur = second;
+                    } else {
+                        if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);
+                        break;
+                    }
+                    if (MRT_REF_TYPE(cur) != MRT_T_NODE2) { descend = true; break; }
+                }
                 break;
             }
             case MRT_T_TRILEAF: {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
                 const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
+                ret = false;
                 for (uint32_t i = 0; i < count; i++) {
                     if (cnt) cnt->tri++;
                     if (hit_triangle(sc, first + i, ray, tmin, tmax, !probe, rec)) {
@@ -483,6 +462,7 @@ MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, fl
             }
             case MRT_T_TRANSLATE:     // scene_object.cpp:9-18
             case MRT_T_ROTATE_Y: {    // scene_object.cpp:70-98
+                ret = false;
                 MrtF4 r0, r2;
                 if (type == MRT_T_ROTATE_Y) {
                     r0 = ld4(sc.rot, 3 * idx);
@@ -516,7 +496,8 @@ MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, fl
                 }
                 ray.inside = 0;
                 ray_set_dir(ray, d);   // the ray ctor re-normalises (ray.h:30); isInside resets to 0
-                next = f2u(r0.w);
+                cur = f2u(r0.w);
+                descend = true;
                 break;
             }
             case MRT_T_VOLUME: {      // volumes.cpp:5-36, first probe
@@ -527,32 +508,30 @@ MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, fl
                 probe = true;
                 tmin = -FLT_MAX;
                 tmax = FLT_MAX;
-                next = f2u(vl.x);
+                cur = f2u(vl.x);
+                descend = true;
                 break;
             }
             default:
+                ret = false;
                 break;
             }
-            cur = next;
-            continue;
         }
 
-        // ---------------------------------------------------------------- return
-        {
+        // ----------------------------------------------------------- return
+        for (;;) {
+            if (st.sp == sp0) return ret && !probe;
             uint32_t e = st.pop();
             uint32_t tag = e >> 29;
             if (tag == MRT_F_IF_MISS) {
-                // the closer child has reported: a hit ends the whole tree (drop every pending farther child)
-                if (ret) {
-                    while (st.sp != sp0 && (st.base[(st.sp - 1) * st.stride] >> 29) == MRT_F_IF_MISS) st.sp--;
-                } else {
-                    cur = e & 0x0FFFFFFFu;
-                }
+                if (ret) continue;
+                cur = e & 0x0FFFFFFFu;
+                break;
             } else if (tag == MRT_F_LIST) {
                 // closest-hit loop over the children (scene_object.h:88-95); primitives inline
                 uint32_t ci = e & 0x0FFFFFFFu;
                 bool found = ((e >> 28) & 1u) | (ret ? 1u : 0u);
-                ret = found;
+                bool composite = false;
                 for (;;) {
                     uint32_t c = ldu(sc.child, ci);
                     uint32_t ctype = MRT_REF_TYPE(c);
@@ -567,10 +546,13 @@ MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, fl
                     } else {
                         st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
                         cur = c;
+                        composite = true;
                         break;
                     }
-                    ret = found;
                 }
+                if (composite) break;
+                ret = found;
+                continue;
             } else if (tag == MRT_F_XLATE_END || tag == MRT_F_ROT_END) {
                 ray.inside = (int) st.pop();
                 ray.inv.z = st.popf(); ray.inv.y = st.popf(); ray.inv.x = st.popf();
@@ -593,46 +575,46 @@ MRT_HD bool intersect(const SceneView &sc, bool valid, Ray &ray, float tmin0, fl
                         rec.n = n;
                     }
                 }
+                continue;
             } else if (tag == MRT_F_VOL1) {
                 uint32_t idx = e & 0x0FFFFFFFu;
                 if (!ret) {
                     probe = false; tmin = tmin0; tmax = main_tmax;
-                } else {
-                    vol_t1 = tmax;   // rec1.t
-                    st.push(MRT_FRAME(MRT_F_VOL2, idx));
-                    tmin = vol_t1 + 0.0001f;
-                    tmax = FLT_MAX;
-                    cur = f2u(ld4(sc.vol, idx).x);
+                    continue;
                 }
+                vol_t1 = tmax;   // rec1.t
+                st.push(MRT_FRAME(MRT_F_VOL2, idx));
+                tmin = vol_t1 + 0.0001f;
+                tmax = FLT_MAX;
+                cur = f2u(ld4(sc.vol, idx).x);
+                break;
             } else {   // MRT_F_VOL2
                 uint32_t idx = e & 0x0FFFFFFFu;
                 float t2 = tmax;
                 bool both = ret;
                 probe = false; tmin = tmin0; tmax = main_tmax;
                 ret = false;
-                if (both) {
-                    float t1 = vol_t1;
-                    if (t1 < tmin) t1 = tmin;
-                    if (t2 > tmax) t2 = tmax;
-                    if (!(t1 >= t2)) {
-                        if (t1 < 0) t1 = 0;
-                        MrtF4 vl = ld4(sc.vol, idx);
-                        float inside_dist = (t2 - t1);
-                        float hit_dist = -(fdiv(1, vl.y)) * cr_logf(randf(rng));
-                        if (hit_dist < inside_dist) {
-                            rec.t = t1 + hit_dist;
-                            rec.p = ray_eval(ray, rec.t);
-                            rec.n = v3(1, 0, 0);
-                            rec.mat = f2u(vl.z);
-                            tmax = rec.t;
-                            ret = true;
-                        }
-                    }
+                if (!both) continue;
+                float t1 = vol_t1;
+                if (t1 < tmin) t1 = tmin;
+                if (t2 > tmax) t2 = tmax;
+                if (t1 >= t2) continue;
+                if (t1 < 0) t1 = 0;
+                MrtF4 vl = ld4(sc.vol, idx);
+                float inside_dist = (t2 - t1);
+                float hit_dist = -(fdiv(1, vl.y)) * cr_logf(randf(rng));
+                if (hit_dist < inside_dist) {
+                    rec.t = t1 + hit_dist;
+                    rec.p = ray_eval(ray, rec.t);
+                    rec.n = v3(1, 0, 0);
+                    rec.mat = f2u(vl.z);
+                    tmax = rec.t;
+                    ret = true;
                 }
+                continue;
             }
         }
     }
-    return valid && ret;
 }
 
 // ------------------------------------------------------------------- textures

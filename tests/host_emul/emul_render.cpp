@@ -89,7 +89,7 @@ int main(int argc, char **argv) {
                         Hit rec;
                         Stack st;
                         st.base = stack_mem.data(); st.stride = 1; st.sp = 0;
-                        bool hit = intersect(sv, true, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
+                        bool hit = intersect(sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
                         if (st.sp != 0) { fprintf(stderr, "stack imbalance\n"); abort(); }
                         if (!path_shade(sv, p, hit, rec, depth, rng)) break;
                     }

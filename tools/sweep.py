@@ -31,7 +31,8 @@ def measure(case, minb, chunk, reps=2):
             best = st
     r.close(); hs.close()
     return {"case": case, "minb": minb, "chunk": chunk, "kernel_ms": best["kernel_ms"], "grays_per_s": best["rays"] / best["kernel_ms"] / 1e6,
-            "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"]}
+            "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"],
+            "alive_frac": best["rays"] / max(1, 32 * best["warp_iterations"])}
 
 
 if __name__ == "__main__":
