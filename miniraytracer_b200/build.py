@@ -18,8 +18,8 @@ LIB = os.path.join(ROOT, "miniraytracer_b200", "libmrt_b200.so")
 EXE = os.path.join(ROOT, "miniraytracer_b200", "mrt_b200")
 
 HOST_SRCS = ["scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "scene_dump.cpp", "flatten.cpp", "host_api.cpp"]
-CUDA_SRCS = ["render_kernel.cu"]
-HEADERS = ["scene_graph.h", "trace_core.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
+CUDA_SRCS = ["render_kernel.cu", "render_wavefront.cu"]
+HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
 
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

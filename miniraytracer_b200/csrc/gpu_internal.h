@@ -1,0 +1,70 @@
+// Internal state shared by the device-side translation units (render_kernel.cu, render_wavefront.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "mrt_gpu.h"
+#include "trace_core.h"
+
+namespace mrt {
+void set_error(const std::string &msg);   // host_api.cpp
+constexpr int kBlock = 128;
+}  // namespace mrt
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            mrt::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+            return MRT_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+struct MrtScene {
+    int device = 0;
+    int sm_count = 0;
+    std::vector<void *> allocs;
+    mrt::SceneView view;
+    uint32_t stack_words = 0;
+    int min_blocks = 6;           // launch-bounds variant (MRT_MINB, tuning knob)
+    uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
+    uint32_t sync_threads = 0;    // block size of the phase-synchronised variant (MRT_SYNC, 0 = off)
+    cudaStream_t stream = nullptr;
+    cudaStream_t poll_stream = nullptr;
+    // accumulator
+    float4 *own_acc = nullptr;
+    size_t own_acc_pixels = 0;
+    float4 *ext_acc = nullptr;
+    uint32_t ext_w = 0, ext_h = 0;
+    float4 *final_buf = nullptr;
+    size_t final_pixels = 0;
+    uint32_t *argb_buf = nullptr;
+    // control block
+    unsigned int *ticket = nullptr;
+    unsigned long long *counters = nullptr;
+    unsigned int *max_bits = nullptr;
+    int *cancel_dev = nullptr;    // device flag polled by lane 0 when it takes a ticket (L2 hit)
+    int *cancel_pinned = nullptr; // pinned staging word for the async write
+    unsigned long long *poll_host = nullptr;   // pinned: [0] ticket [1] rays
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // last render
+    bool rendered = false;
+    MrtRenderParams last;
+    uint32_t last_tasks = 0, last_grid = 0, last_block = mrt::kBlock, last_smem = 0, last_mode = 0;
+    float4 *last_acc = nullptr;
+    uint64_t last_rays = 0, last_iters = 0, last_nonfinite = 0;   // filled by the wavefront driver (it is synchronous)
+    bool last_wavefront = false;
+    // wavefront renderer state (render_wavefront.cu)
+    uint32_t has_volumes = 0;
+    int wavefront = 0;            // MRT_WAVEFRONT: 1 = use the wavefront renderer
+    void *wf_state = nullptr;
+    size_t wf_state_bytes = 0;
+    unsigned int *wf_ctrl = nullptr;
+};
+
+// render_wavefront.cu
+int mrt_wavefront_render(MrtScene *s, const MrtRenderParams *p, float4 *acc, uint32_t sqrt_n);
+void mrt_wavefront_free(MrtScene *s);
+

@@ -15,7 +15,7 @@
 
 #ifdef __CUDACC__
 #define MRT_LIBM_HD __host__ __device__ __forceinline__
-#define MRT_LIBM_FN __host__ __device__ __noinline__   /* double-precision bodies are large: one copy each */
+#define MRT_LIBM_FN __host__ __device__ __forceinline__   /* every function below has exactly one call site in the kernels */
 #else
 #define MRT_LIBM_HD inline
 #define MRT_LIBM_FN inline

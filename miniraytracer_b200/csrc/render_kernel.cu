@@ -28,12 +28,9 @@
 #include <string>
 #include <vector>
 
-#include "mrt_gpu.h"
-#include "trace_core.h"
+#include "gpu_internal.h"
 
 namespace mrt {
-
-void set_error(const std::string &msg);   // host_api.cpp
 
 struct RenderArgs {
     SceneView sc;
@@ -48,7 +45,6 @@ struct RenderArgs {
     const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
 };
 
-constexpr int kBlock = 128;
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -395,49 +391,6 @@ __global__ void tonemap_kernel(const float4 *img, uint32_t *argb, uint32_t n, co
 // =========================================================================
 using namespace mrt;
 
-#define CUDA_TRY(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess) {                                                                    \
-            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
-            return MRT_E_CUDA;                                                                      \
-        }                                                                                           \
-    } while (0)
-
-struct MrtScene {
-    int device = 0;
-    int sm_count = 0;
-    std::vector<void *> allocs;
-    SceneView view;
-    uint32_t stack_words = 0;
-    int min_blocks = 6;           // launch-bounds variant (MRT_MINB, tuning knob)
-    uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
-    uint32_t sync_threads = 0;    // block size of the phase-synchronised variant (MRT_SYNC, 0 = off)
-    cudaStream_t stream = nullptr;
-    cudaStream_t poll_stream = nullptr;
-    // accumulator
-    float4 *own_acc = nullptr;
-    size_t own_acc_pixels = 0;
-    float4 *ext_acc = nullptr;
-    uint32_t ext_w = 0, ext_h = 0;
-    float4 *final_buf = nullptr;
-    size_t final_pixels = 0;
-    uint32_t *argb_buf = nullptr;
-    // control block
-    unsigned int *ticket = nullptr;
-    unsigned long long *counters = nullptr;
-    unsigned int *max_bits = nullptr;
-    int *cancel_dev = nullptr;    // device flag polled by lane 0 when it takes a ticket (L2 hit)
-    int *cancel_pinned = nullptr; // pinned staging word for the async write
-    unsigned long long *poll_host = nullptr;   // pinned: [0] ticket [1] rays
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // last render
-    bool rendered = false;
-    MrtRenderParams last;
-    uint32_t last_tasks = 0, last_grid = 0, last_block = kBlock, last_smem = 0, last_mode = 0;
-    float4 *last_acc = nullptr;
-};
-
 template <typename T>
 static int upload(MrtScene *s, const T *host, size_t count, const T **dev) {
     *dev = nullptr;
@@ -489,6 +442,7 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->rendered) cudaStreamSynchronize(s->stream);
+    mrt_wavefront_free(s);
     for (void *p : s->allocs) cudaFree(p);
     if (s->own_acc) cudaFree(s->own_acc);
     if (s->final_buf) cudaFree(s->final_buf);
@@ -542,6 +496,8 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
     if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
     if (const char *e = getenv("MRT_SYNC")) s->sync_threads = (uint32_t) atoi(e);
+    if (const char *e = getenv("MRT_WAVEFRONT")) s->wavefront = atoi(e);
+    s->has_volumes = d->n_vol ? 1u : 0u;
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -603,6 +559,19 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
             CUDA_TRY(cudaMemsetAsync(s->own_acc, 0, (size_t) n_pixels * sizeof(float4), s->stream));
         }
         acc = s->own_acc;
+    }
+
+    if (s->wavefront) {   // wavefront renderer (render_wavefront.cu); synchronous host loop
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+        CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+        int rc = mrt_wavefront_render(s, p, acc, sq);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+        s->rendered = true;
+        s->last = *p;
+        s->last_tasks = 1; s->last_grid = 0; s->last_block = 128; s->last_smem = 0; s->last_mode = 2u;
+        s->last_acc = acc;
+        return MRT_OK;
     }
 
     RenderArgs a;

@@ -45,6 +45,7 @@ int main(int argc, char **argv) {
     std::string assets = argval(argc, argv, "-assets", "assets");
     const char *out = argval(argc, argv, "-out", nullptr);
     bool want_counters = argflag(argc, argv, "-counters");
+    bool stepper = argflag(argc, argv, "-stepper");   // incremental traversal (trav_step) instead of intersect()
 
     SceneGraph g;
     if (!build_scene(g, scene, float(W) / float(H), assets)) { fprintf(stderr, "scene: %s\n", g.error.c_str()); return 1; }
@@ -89,7 +90,15 @@ int main(int argc, char **argv) {
                         Hit rec;
                         Stack st;
                         st.base = stack_mem.data(); st.stride = 1; st.sp = 0;
-                        bool hit = intersect(sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
+                        bool hit;
+                        if (stepper) {
+                            Trav tr;
+                            trav_begin(sv, tr, 0.001f, FLT_MAX, st);
+                            while (trav_active(tr, st)) trav_step(sv, tr, p.ray, rec, rng, st, want_counters ? &cnt : nullptr);
+                            hit = trav_hit(tr);
+                        } else {
+                            hit = intersect(sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
+                        }
                         if (st.sp != 0) { fprintf(stderr, "stack imbalance\n"); abort(); }
                         if (!path_shade(sv, p, hit, rec, depth, rng)) break;
                     }

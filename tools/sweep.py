@@ -41,12 +41,16 @@ if __name__ == "__main__":
     ap.add_argument("--minb", default="5")
     ap.add_argument("--chunk", default="0")
     ap.add_argument("--sync", default="0")
+    ap.add_argument("--wavefront", default="0")
     args = ap.parse_args()
     for case in args.cases.split(","):
         for minb in args.minb.split(","):
             for chunk in args.chunk.split(","):
                 for sync in args.sync.split(","):
-                    os.environ["MRT_SYNC"] = sync
-                    res = measure(case, int(minb), int(chunk))
-                    res["sync"] = int(sync)
-                    print(json.dumps(res), flush=True)
+                    for wf in args.wavefront.split(","):
+                        os.environ["MRT_SYNC"] = sync
+                        os.environ["MRT_WAVEFRONT"] = wf
+                        res = measure(case, int(minb), int(chunk))
+                        res["sync"] = int(sync)
+                        res["wavefront"] = int(wf)
+                        print(json.dumps(res), flush=True)
