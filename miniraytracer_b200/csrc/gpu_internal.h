@@ -28,7 +28,8 @@ struct MrtScene {
     std::vector<void *> allocs;
     mrt::SceneView view;
     uint32_t stack_words = 0;
-    int min_blocks = 6;           // launch-bounds variant (MRT_MINB, tuning knob)
+    int min_blocks = 0;           // launch-bounds variant (MRT_MINB); 0 = by scene: 5 (96 regs) with BVH trees, else 6 (80 regs)
+    uint32_t has_trees = 0;
     uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
     uint32_t sync_threads = 0;    // block size of the phase-synchronised variant (MRT_SYNC, 0 = off)
     cudaStream_t stream = nullptr;

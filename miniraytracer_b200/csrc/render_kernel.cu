@@ -498,6 +498,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (const char *e = getenv("MRT_SYNC")) s->sync_threads = (uint32_t) atoi(e);
     if (const char *e = getenv("MRT_WAVEFRONT")) s->wavefront = atoi(e);
     s->has_volumes = d->n_vol ? 1u : 0u;
+    s->has_trees = d->n_node2 ? 1u : 0u;
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -588,7 +589,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
     // kernel variant: minimum resident blocks per SM the register allocation is bounded for
-    int minb = s->min_blocks;
+    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 6);   // measured: profiles/r1_notes.md
     typedef void (*kernel_t)(const RenderArgs);
     kernel_t kernel = nullptr;
     uint32_t threads = kBlock;
@@ -602,6 +603,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         switch (minb) {
         case 4: kernel = mode_w ? render_pixel_per_warp<4> : render_pixel_per_lane<4>; break;
         case 6: kernel = mode_w ? render_pixel_per_warp<6> : render_pixel_per_lane<6>; break;
+        case 7: kernel = mode_w ? render_pixel_per_warp<7> : render_pixel_per_lane<7>; break;
         case 8: kernel = mode_w ? render_pixel_per_warp<8> : render_pixel_per_lane<8>; break;
         default: minb = 5; kernel = mode_w ? render_pixel_per_warp<5> : render_pixel_per_lane<5>; break;
         }

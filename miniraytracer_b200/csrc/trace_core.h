@@ -976,11 +976,22 @@ MRT_FN float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time)
 }
 
 struct Onb { V3 u, v, w; };   // onb.h:19-27
+// x / len for the onb construction.  cross(w, a) with an axis vector a always has one component that is
+// exactly +-0 (two for axis-aligned surface normals); 0 / len is that same signed zero for any positive
+// finite len, so the IEEE division -- whose zero-numerator case takes the slow path of __fdiv_rn
+// (ncu round 1: 0.83 slow-path calls per ray in the Cornell box) -- is skipped for it.
+MRT_HD float fdiv_zero_num(float x, float len, bool len_ok) {
+    if (len_ok && x == 0.0f) return x;
+    return fdiv(x, len);
+}
 MRT_HD Onb make_onb(V3 n) {
     Onb o;
     o.w = n;
     V3 a = (fabsf(n.x) > 0.9f) ? v3(0, 1, 0) : v3(1, 0, 0);
-    o.v = normalize(cross(o.w, a));
+    V3 c = cross(o.w, a);
+    float len = fsqrt(sdot(c));
+    bool ok = (len > 0.0f) && (len < INFINITY);
+    o.v = v3(fdiv_zero_num(c.x, len, ok), fdiv_zero_num(c.y, len, ok), fdiv_zero_num(c.z, len, ok));   // normalize(c)
     o.u = cross(o.w, o.v);
     return o;
 }
