@@ -28,3 +28,8 @@ if __name__ == "__main__":
         print("scene", scene, "rays", meta["rays"])
     kat = oracle_util.ref_run(["kat"]).stdout
     open(os.path.join(HERE, "kat.txt"), "w").write(kat)
+    # scene dumps printed by the reference + matching renders, used to test oracle/mrt_oracle.c without the reference binary
+    for scene in (2, 3, 5, 6):
+        oracle_util.ref_dump_scene(scene, 200, 160, os.path.join(HERE, f"scene{scene}_dump_200x160.txt"))
+        acc, meta = oracle_util.ref_render(scene, 200, 160, 4)
+        np.savez_compressed(os.path.join(HERE, f"golden_restatement_scene{scene}.npz"), acc=acc, rays=np.uint64(meta["rays"]))
