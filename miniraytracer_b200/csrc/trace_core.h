@@ -442,14 +442,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                         cur = second;
                     } else {
                         if (cnt) cnt->aabb += ((lfirst ? flags >> 1 : flags) & 1u);
-                        // both children missed: this subtree reports no hit.  If the frame on top of the stack
-                        // is a pending farther child of this tree, resume with it right here (the lane stays
-                        // in the inner loop instead of going through the generic return path).
-                        if (st.sp == sp0) break;
-                        const uint32_t e = st.base[(st.sp - 1) * st.stride];
-                        if ((e >> 29) != MRT_F_IF_MISS) break;
-                        st.sp--;
-                        cur = e & 0x0FFFFFFFu;
+                        break;
                     }
                     if (MRT_REF_TYPE(cur) != MRT_T_NODE2) { descend = true; break; }
                 }
