@@ -134,11 +134,19 @@ struct Flattener {
         default: *has_box = false; *box = Aabb(); return wrap(node(id));   // spheres, transforms, ...: no box test of their own here
         }
     }
-    void push_node2(const Aabb &lb, bool lhas, uint32_t l, const Aabb &rb, bool rhas, uint32_t r, uint8_t order) {
-        o.node2.push_back(f4(lb.min.x, lb.min.y, lb.min.z, ubits(l | ((uint32_t) (order & 15u) << 28))));
-        o.node2.push_back(f4(lb.max.x, lb.max.y, lb.max.z, ubits(r | ((uint32_t) (order >> 4) << 28))));
-        o.node2.push_back(f4(rb.min.x, rb.min.y, rb.min.z, ubits((lhas ? 1u : 0u) | (rhas ? 2u : 0u))));
-        o.node2.push_back(f4(rb.max.x, rb.max.y, rb.max.z, 0));
+    // nodes are laid out in depth-first PRE-order (a node right before its first subtree): a traversal that
+    // descends keeps touching neighbouring 64-byte records (L1 hit rate of the triangle scene was 69 % with
+    // post-order placement)
+    uint32_t reserve_node2() {
+        uint32_t i = (uint32_t) o.node2.size() / 4;
+        for (int k = 0; k < 4; k++) o.node2.push_back(f4(0, 0, 0, 0));
+        return i;
+    }
+    void fill_node2(uint32_t i, const Aabb &lb, bool lhas, uint32_t l, const Aabb &rb, bool rhas, uint32_t r, uint8_t order) {
+        o.node2[4 * i + 0] = f4(lb.min.x, lb.min.y, lb.min.z, ubits(l | ((uint32_t) (order & 15u) << 28)));
+        o.node2[4 * i + 1] = f4(lb.max.x, lb.max.y, lb.max.z, ubits(r | ((uint32_t) (order >> 4) << 28)));
+        o.node2[4 * i + 2] = f4(rb.min.x, rb.min.y, rb.min.z, ubits((lhas ? 1u : 0u) | (rhas ? 2u : 0u)));
+        o.node2[4 * i + 3] = f4(rb.max.x, rb.max.y, rb.max.z, 0);
     }
     std::map<int, uint32_t> inner_memo;
     uint32_t bvh_inner(int id) {
@@ -147,11 +155,11 @@ struct Flattener {
         const Node &n = g.nodes[id];
         Aabb lb, rb;
         bool lhas = false, rhas = false;
-        uint32_t l = bvh_child(n.left, &lb, &lhas), r = bvh_child(n.right, &rb, &rhas);
-        uint32_t i = (uint32_t) o.node2.size() / 4;
-        push_node2(lb, lhas, l, rb, rhas, r, n.order);
+        uint32_t i = reserve_node2();
         uint32_t ref = MRT_REF(MRT_T_NODE2, i);
         inner_memo[id] = ref;
+        uint32_t l = bvh_child(n.left, &lb, &lhas), r = bvh_child(n.right, &rb, &rhas);
+        fill_node2(i, lb, lhas, l, rb, rhas, r, n.order);
         return ref;
     }
     uint32_t pod_child(const Mesh &mesh, uint32_t ni, uint32_t tri_base) {
@@ -162,9 +170,9 @@ struct Flattener {
             o.trileaf.push_back(pn.prim_count);
             return MRT_REF(MRT_T_TRILEAF, i);
         }
+        uint32_t i = reserve_node2();
         uint32_t l = pod_child(mesh, pn.left, tri_base), r = pod_child(mesh, pn.left + 1, tri_base);
-        uint32_t i = (uint32_t) o.node2.size() / 4;
-        push_node2(mesh.nodes[pn.left].box, true, l, mesh.nodes[pn.left + 1].box, true, r, pn.order);
+        fill_node2(i, mesh.nodes[pn.left].box, true, l, mesh.nodes[pn.left + 1].box, true, r, pn.order);
         return MRT_REF(MRT_T_NODE2, i);
     }
 

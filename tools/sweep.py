@@ -42,6 +42,7 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", default="0")
     ap.add_argument("--sync", default="0")
     ap.add_argument("--wavefront", default="0")
+    ap.add_argument("--prefetch", default="0")
     args = ap.parse_args()
     for case in args.cases.split(","):
         for minb in args.minb.split(","):
@@ -49,8 +50,11 @@ if __name__ == "__main__":
                 for sync in args.sync.split(","):
                     for wf in args.wavefront.split(","):
                         os.environ["MRT_SYNC"] = sync
-                        os.environ["MRT_WAVEFRONT"] = wf
-                        res = measure(case, int(minb), int(chunk))
-                        res["sync"] = int(sync)
-                        res["wavefront"] = int(wf)
-                        print(json.dumps(res), flush=True)
+                        for pf in args.prefetch.split(","):
+                            os.environ["MRT_WAVEFRONT"] = wf
+                            os.environ["MRT_PREFETCH"] = pf
+                            res = measure(case, int(minb), int(chunk))
+                            res["sync"] = int(sync)
+                            res["wavefront"] = int(wf)
+                            res["prefetch"] = int(pf)
+                            print(json.dumps(res), flush=True)
