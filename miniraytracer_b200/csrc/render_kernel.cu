@@ -491,8 +491,6 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     v.root = d->root;
     v.n_lights = d->n_lights;
     v.sky = d->sky;
-    v.flags = 0;
-    if (const char *e = getenv("MRT_PREFETCH")) v.flags |= (atoi(e) ? 1u : 0u);
     v.cam = d->camera;
     s->stack_words = d->stack_words ? d->stack_words : 64;
     if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);

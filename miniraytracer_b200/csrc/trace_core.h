@@ -221,7 +221,6 @@ struct SceneView {
     const int32_t *perlin_perm;
     const uint8_t *image;
     uint32_t root, n_lights, sky;
-    uint32_t flags;   // bit 0: prefetch both child nodes of an inner node (tuning knob)
     MrtCamera cam;
 };
 
@@ -428,12 +427,6 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                     const uint32_t w0 = f2u(n0.w), w1 = f2u(n1.w), flags = f2u(n2.w);
                     const uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
                     const uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
-#ifdef __CUDA_ARCH__
-                    if (sc.flags & 1u) {   // start fetching both children while this node's boxes are tested
-                        if (MRT_REF_TYPE(left) == MRT_T_NODE2) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.node2 + 4 * MRT_REF_INDEX(left)));
-                        if (MRT_REF_TYPE(right) == MRT_T_NODE2) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.node2 + 4 * MRT_REF_INDEX(right)));
-                    }
-#endif
                     const bool hl = !(flags & 1u) || aabb_hit(n0, n1, ray, tmin, tmax);
                     const bool hr = !(flags & 2u) || aabb_hit(n2, n3, ray, tmin, tmax);
                     const bool lfirst = (order & ray.mask) != 0;

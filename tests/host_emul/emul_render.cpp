@@ -56,7 +56,7 @@ int main(int argc, char **argv) {
     sv.sphere = d.sphere; sv.rect = d.rect; sv.list = d.list; sv.bvh = d.bvh; sv.node2 = d.node2; sv.trileaf = d.trileaf; sv.tri = d.tri; sv.trin = d.trin;
     sv.xlate = d.xlate; sv.rot = d.rot; sv.vol = d.vol; sv.mat = d.mat; sv.tex = d.tex; sv.perlin_vec = d.perlin_vec;
     sv.child = d.child; sv.lights = d.lights; sv.perlin_perm = d.perlin_perm; sv.image = d.image;
-    sv.flags = 0; sv.root = d.root; sv.n_lights = d.n_lights; sv.sky = d.sky; sv.cam = d.camera;
+    sv.root = d.root; sv.n_lights = d.n_lights; sv.sky = d.sky; sv.cam = d.camera;
 
     uint32_t sq = (uint32_t) sqrtf((float) spp);
     uint32_t N = sq * sq;
