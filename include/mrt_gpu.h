@@ -70,6 +70,11 @@ int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHos
 const MrtSceneDesc *mrt_scene_desc(const MrtHostScene *s);
 /* Canonical text dump of the scene graph (same format as the oracle's dump-scene). */
 int mrt_scene_dump(const MrtHostScene *s, const char *path);
+/* Flattened-scene file ("MRTSCN1"): every table of MrtSceneDesc, so that OBJ parsing, image decoding and the
+ * BVH builds (obj_loader.cpp, triangle.h:77-168, scene_object.h:282-319) need not be repeated -- SURVEY.md 8(f)3.
+ * A loaded scene has a description but no graph (mrt_scene_dump is not available for it). */
+int mrt_scene_save(const MrtHostScene *s, const char *path);
+int mrt_scene_load(const char *path, MrtHostScene **out);
 void mrt_scene_free(MrtHostScene *s);
 
 /* ----------------------------------------------------------------- device side

@@ -75,7 +75,7 @@ DEFAULT_SEED = 11350390909718046443  # main.cpp:302
 # every symbol include/mrt_gpu.h declares
 EXPORTS = [
     "mrt_last_error", "mrt_params_default", "mrt_params_parse", "mrt_scene_create", "mrt_scene_desc",
-    "mrt_scene_dump", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_stream",
+    "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_stream",
     "mrt_gpu_bind_accumulator", "mrt_gpu_render_async", "mrt_gpu_poll", "mrt_gpu_wait", "mrt_gpu_stats",
     "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_cancel", "mrt_gpu_destroy",
 ]
@@ -112,6 +112,8 @@ def load(build_if_missing=True):
     lib.mrt_scene_desc.argtypes = [vp]
     lib.mrt_scene_desc.restype = C.POINTER(SceneDesc)
     lib.mrt_scene_dump.argtypes = [vp, C.c_char_p]
+    lib.mrt_scene_save.argtypes = [vp, C.c_char_p]
+    lib.mrt_scene_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.mrt_scene_free.argtypes = [vp]
     lib.mrt_scene_free.restype = None
     lib.mrt_gpu_init.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
@@ -159,14 +161,25 @@ def grid_samples(spp):
 class HostScene:
     """Host-built + flattened scene (mrt_scene_create). Usable without a GPU."""
 
-    def __init__(self, scene, width, height, asset_dir=None):
+    def __init__(self, scene, width, height, asset_dir=None, path=None):
         lib = load()
         self._lib = lib
         self._h = C.c_void_p()
+        if path is not None:   # flattened scene file written by save()
+            _check(lib.mrt_scene_load(str(path).encode(), C.byref(self._h)))
+            self.scene = None
+            return
         aspect = np.float32(width) / np.float32(height)
         _check(lib.mrt_scene_create(int(scene), C.c_float(aspect), (asset_dir or default_asset_dir()).encode(),
                                     C.byref(self._h)))
         self.scene = int(scene)
+
+    @classmethod
+    def load(cls, path):
+        return cls(None, 0, 0, path=path)
+
+    def save(self, path):
+        _check(self._lib.mrt_scene_save(self._h, str(path).encode()))
 
     @property
     def desc(self):

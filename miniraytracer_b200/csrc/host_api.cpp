@@ -134,6 +134,7 @@ extern "C" int mrt_params_parse(int argc, char **argv, MrtParams *out) {
 struct MrtHostScene {
     SceneGraph graph;
     FlatScene flat;
+    bool has_graph = true;
 };
 
 extern "C" int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHostScene **out) {
@@ -160,10 +161,78 @@ extern "C" const MrtSceneDesc *mrt_scene_desc(const MrtHostScene *s) { return s 
 
 extern "C" int mrt_scene_dump(const MrtHostScene *s, const char *path) {
     if (!s || !path) { set_error("mrt_scene_dump: null argument"); return MRT_E_INVALID; }
+    if (!s->has_graph) { set_error("mrt_scene_dump: scene was loaded from a flattened file (no graph)"); return MRT_E_STATE; }
     FILE *f = fopen(path, "w");
     if (!f) { set_error(std::string("cannot open ") + path); return MRT_E_INVALID; }
     dump_scene(s->graph, f);
     fclose(f);
+    return MRT_OK;
+}
+
+// ---------------------------------------------------------------- scene file
+namespace {
+const char kMagic[8] = {'M', 'R', 'T', 'S', 'C', 'N', '1', 0};
+template <typename T> bool put(FILE *f, const std::vector<T> &v) {
+    uint64_t n = v.size();
+    return fwrite(&n, sizeof(n), 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <typename T> bool get(FILE *f, std::vector<T> &v) {
+    uint64_t n = 0;
+    if (fread(&n, sizeof(n), 1, f) != 1 || n > (1ull << 34) / sizeof(T)) return false;
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+void rebind(FlatScene &o) {   // pointers of the description follow the vectors
+    MrtSceneDesc &d = o.desc;
+    d.lights = o.lights.data();
+    d.sphere = o.sphere.data(); d.rect = o.rect.data(); d.list = o.list.data(); d.child = o.child.data();
+    d.bvh = o.bvh.data(); d.node2 = o.node2.data(); d.trileaf = o.trileaf.data(); d.tri = o.tri.data(); d.trin = o.trin.data();
+    d.xlate = o.xlate.data(); d.rot = o.rot.data(); d.vol = o.vol.data(); d.mat = o.mat.data(); d.tex = o.tex.data();
+    d.perlin_vec = o.perlin_vec.empty() ? nullptr : o.perlin_vec.data();
+    d.perlin_perm = o.perlin_perm.empty() ? nullptr : o.perlin_perm.data();
+    d.image = o.image.empty() ? nullptr : o.image.data();
+}
+}  // namespace
+
+extern "C" int mrt_scene_save(const MrtHostScene *s, const char *path) {
+    if (!s || !path) { set_error("mrt_scene_save: null argument"); return MRT_E_INVALID; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error(std::string("cannot open ") + path); return MRT_E_INVALID; }
+    const FlatScene &o = s->flat;
+    MrtSceneDesc d = o.desc;   // scalar part; pointers are meaningless in the file
+    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&d, sizeof(d), 1, f) == 1;
+    ok = ok && put(f, o.sphere) && put(f, o.rect) && put(f, o.list) && put(f, o.child) && put(f, o.bvh) && put(f, o.node2) &&
+         put(f, o.trileaf) && put(f, o.tri) && put(f, o.trin) && put(f, o.xlate) && put(f, o.rot) && put(f, o.vol) && put(f, o.mat) &&
+         put(f, o.tex) && put(f, o.perlin_vec) && put(f, o.perlin_perm) && put(f, o.image) && put(f, o.lights);
+    fclose(f);
+    if (!ok) { set_error(std::string("short write to ") + path); return MRT_E_INVALID; }
+    return MRT_OK;
+}
+
+extern "C" int mrt_scene_load(const char *path, MrtHostScene **out) {
+    if (!path || !out) { set_error("mrt_scene_load: null argument"); return MRT_E_INVALID; }
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error(std::string("cannot open ") + path); return MRT_E_SCENE; }
+    MrtHostScene *s = new (std::nothrow) MrtHostScene();
+    if (!s) { fclose(f); set_error("out of memory"); return MRT_E_INVALID; }
+    s->has_graph = false;
+    FlatScene &o = s->flat;
+    char magic[8];
+    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&o.desc, sizeof(o.desc), 1, f) == 1;
+    ok = ok && get(f, o.sphere) && get(f, o.rect) && get(f, o.list) && get(f, o.child) && get(f, o.bvh) && get(f, o.node2) &&
+         get(f, o.trileaf) && get(f, o.tri) && get(f, o.trin) && get(f, o.xlate) && get(f, o.rot) && get(f, o.vol) && get(f, o.mat) &&
+         get(f, o.tex) && get(f, o.perlin_vec) && get(f, o.perlin_perm) && get(f, o.image) && get(f, o.lights);
+    fclose(f);
+    const MrtSceneDesc &d = o.desc;
+    ok = ok && o.sphere.size() == (size_t) d.n_sphere * 3 && o.rect.size() == (size_t) d.n_rect * 2 && o.list.size() == (size_t) d.n_list * 2 &&
+         o.child.size() == d.n_child && o.bvh.size() == (size_t) d.n_bvh * 2 && o.node2.size() == (size_t) d.n_node2 * 4 &&
+         o.trileaf.size() == (size_t) d.n_trileaf * 2 && o.tri.size() == (size_t) d.n_tri * 3 && o.trin.size() == o.tri.size() &&
+         o.xlate.size() == d.n_xlate && o.rot.size() == (size_t) d.n_rot * 3 && o.vol.size() == d.n_vol && o.mat.size() == d.n_mat &&
+         o.tex.size() == d.n_tex && o.image.size() == d.n_image_bytes && o.lights.size() == d.n_lights;
+    if (!ok) { delete s; set_error(std::string("not a valid MRTSCN1 file: ") + path); return MRT_E_SCENE; }
+    rebind(o);
+    *out = s;
     return MRT_OK;
 }
 

@@ -72,17 +72,29 @@ int main(int argc, char **argv) {
         }
     }
     double t1 = now_s();
-    for (uint32_t g = 0; g < G; g++) {
-        MrtRenderParams rp;
-        memset(&rp, 0, sizeof(rp));
-        rp.width = W; rp.height = H; rp.samples = N;
-        rp.sample_begin = (uint32_t) ((uint64_t) N * g / G);
-        rp.sample_end = (uint32_t) ((uint64_t) N * (g + 1) / G);
-        rp.max_bounces = p.max_bounces;
-        rp.seed = p.seed;
-        rp.max_luminance = p.max_luminance;
-        mrt_gpu_init((int) g, nullptr);
-        if (mrt_gpu_render_async(scenes[g], &rp)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+    // -mode 0 (work_queue_seq, main.cpp:347-349): all samples of a GPU's slice in one launch.
+    // -mode 1 (work_queue_dynamic + draw2, main.cpp:350-354,193-243): sample-major passes, the image refines
+    // progressively; here each pass is one launch that ACCUMULATES a slice of the samples (sum + count, so the
+    // running mean of draw2 is the finalised accumulator after every pass).
+    const uint32_t passes = (p.threading_mode == 1) ? 8u : 1u;
+    for (uint32_t pass = 0; pass < passes; pass++) {
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t g0 = (uint32_t) ((uint64_t) N * g / G), g1 = (uint32_t) ((uint64_t) N * (g + 1) / G);
+            MrtRenderParams rp;
+            memset(&rp, 0, sizeof(rp));
+            rp.width = W; rp.height = H; rp.samples = N;
+            rp.sample_begin = g0 + (uint32_t) ((uint64_t) (g1 - g0) * pass / passes);
+            rp.sample_end = g0 + (uint32_t) ((uint64_t) (g1 - g0) * (pass + 1) / passes);
+            if (rp.sample_begin == rp.sample_end) continue;
+            rp.max_bounces = p.max_bounces;
+            rp.seed = p.seed;
+            rp.max_luminance = p.max_luminance;
+            rp.flags = pass ? MRT_RENDER_ACCUMULATE : 0u;
+            mrt_gpu_init((int) g, nullptr);
+            if (pass) mrt_gpu_wait(scenes[g]);
+            if (mrt_gpu_render_async(scenes[g], &rp)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+        }
+        if (passes > 1) fprintf(stderr, "\rpass %u/%u", pass + 1, passes);
     }
     // poll loop (main.cpp:387-411)
     for (;;) {

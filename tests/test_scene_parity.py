@@ -62,3 +62,31 @@ def test_flat_scene_shapes():
 def test_missing_asset_is_an_error(tmp_path):
     with pytest.raises(api.MrtError):
         api.HostScene(7, 640, 360, asset_dir=str(tmp_path))   # no earthmap.ppm there
+
+
+@pytest.mark.parametrize("scene", [0, 5, 7, 8])
+def test_scene_file_round_trip(scene, tmp_path):
+    """MRTSCN1: every table of the flattened description survives save -> load bit for bit."""
+    import ctypes
+    hs = api.HostScene(scene, 640, 360)
+    path = tmp_path / "scene.mrtscn"
+    hs.save(path)
+    ld = api.HostScene.load(path)
+    a, b = hs.desc.contents, ld.desc.contents
+    for name, ctype in api.SceneDesc._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        if isinstance(va, (int, float)):
+            assert va == vb, name
+    def table(d, name, count, elem):
+        return ctypes.string_at(getattr(d, name), count * elem) if count else b""
+    for name, count, elem in (("sphere", a.n_sphere * 3, 16), ("rect", a.n_rect * 2, 16), ("list", a.n_list * 2, 16), ("child", a.n_child, 4),
+                              ("bvh", a.n_bvh * 2, 16), ("node2", a.n_node2 * 4, 16), ("trileaf", a.n_trileaf * 2, 4), ("tri", a.n_tri * 3, 16),
+                              ("trin", a.n_tri * 3, 16), ("xlate", a.n_xlate, 16), ("rot", a.n_rot * 3, 16), ("vol", a.n_vol, 16),
+                              ("mat", a.n_mat, 16), ("tex", a.n_tex, 16), ("lights", a.n_lights, 4), ("image", a.n_image_bytes, 1)):
+        assert table(a, name, count, elem) == table(b, name, count, elem), name
+    assert ctypes.string_at(ctypes.byref(a.camera), ctypes.sizeof(a.camera)) == ctypes.string_at(ctypes.byref(b.camera), ctypes.sizeof(b.camera))
+    with pytest.raises(api.MrtError):
+        ld.dump(tmp_path / "x.txt")     # a loaded scene has no graph
+    hs.close(); ld.close()
+    with pytest.raises(api.MrtError):
+        api.HostScene.load(tmp_path / "missing.mrtscn")
