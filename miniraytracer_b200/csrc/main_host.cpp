@@ -77,7 +77,22 @@ int main(int argc, char **argv) {
     // progressively; here each pass is one launch that ACCUMULATES a slice of the samples (sum + count, so the
     // running mean of draw2 is the finalised accumulator after every pass).
     const uint32_t passes = (p.threading_mode == 1) ? 8u : 1u;
+    uint64_t rays = 0, paths = 0, dropped = 0;
+    float kernel_ms = 0;
+    auto collect = [&]() -> int {   // statistics of the launches in flight (blocks until they have finished)
+        float ms_max = 0;
+        for (uint32_t g = 0; g < G; g++) {
+            MrtRenderStats st;
+            mrt_gpu_init((int) g, nullptr);
+            if (mrt_gpu_stats(scenes[g], &st)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+            rays += st.rays; paths += st.paths; dropped += st.nonfinite;
+            if (st.kernel_ms > ms_max) ms_max = st.kernel_ms;
+        }
+        kernel_ms += ms_max;
+        return 0;
+    };
     for (uint32_t pass = 0; pass < passes; pass++) {
+        if (pass && collect()) return 1;
         for (uint32_t g = 0; g < G; g++) {
             const uint32_t g0 = (uint32_t) ((uint64_t) N * g / G), g1 = (uint32_t) ((uint64_t) N * (g + 1) / G);
             MrtRenderParams rp;
@@ -91,7 +106,6 @@ int main(int argc, char **argv) {
             rp.max_luminance = p.max_luminance;
             rp.flags = pass ? MRT_RENDER_ACCUMULATE : 0u;
             mrt_gpu_init((int) g, nullptr);
-            if (pass) mrt_gpu_wait(scenes[g]);
             if (mrt_gpu_render_async(scenes[g], &rp)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
         }
         if (passes > 1) fprintf(stderr, "\rpass %u/%u", pass + 1, passes);
@@ -110,15 +124,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "\rTrace: %.2fs (%.0f%%)", el, pct_min);
         std::this_thread::sleep_for(std::chrono::milliseconds(33));
     }
-    uint64_t rays = 0, paths = 0, dropped = 0;
-    float kernel_ms = 0;
-    for (uint32_t g = 0; g < G; g++) {
-        MrtRenderStats st;
-        mrt_gpu_init((int) g, nullptr);
-        if (mrt_gpu_stats(scenes[g], &st)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
-        rays += st.rays; paths += st.paths; dropped += st.nonfinite;
-        if (st.kernel_ms > kernel_ms) kernel_ms = st.kernel_ms;
-    }
+    if (collect()) return 1;
     double secs = now_s() - t1;
     fprintf(stderr, "\r");
     printf("Trace: %.2fs - %.3f Mrays/s | %.6f us/ray | %.3f Mpaths/s | kernel %.1f ms | %llu samples dropped (non-finite)\n", secs,
