@@ -76,7 +76,8 @@ int main(int argc, char **argv) {
     // -mode 1 (work_queue_dynamic + draw2, main.cpp:350-354,193-243): sample-major passes, the image refines
     // progressively; here each pass is one launch that ACCUMULATES a slice of the samples (sum + count, so the
     // running mean of draw2 is the finalised accumulator after every pass).
-    const uint32_t passes = (p.threading_mode == 1) ? 8u : 1u;
+    uint32_t passes = (p.threading_mode == 1) ? 8u : 1u;
+    if (passes > N / G) passes = (N / G) ? (N / G) : 1u;   // at least one sample per pass and GPU
     uint64_t rays = 0, paths = 0, dropped = 0;
     float kernel_ms = 0;
     auto collect = [&]() -> int {   // statistics of the launches in flight (blocks until they have finished)
