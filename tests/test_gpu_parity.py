@@ -165,3 +165,15 @@ def test_poll_and_cancel():
     pct, rays = r.poll()
     assert pct == 100.0 and rays > 0
     r.close(); hs.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 36), (7, 160, 90, 16), (8, 128, 72, 16)])
+def test_wavefront_renderer_parity(scene, w, h, spp, monkeypatch):
+    """The opt-in wavefront renderer (MRT_WAVEFRONT=1: wf_logic + persistent incremental wf_trav) computes the
+    same accumulators as the megakernel -- it runs the same per-path phases of trace_core.h."""
+    ref, meta = oracle_util.ref_render(scene, w, h, spp)
+    monkeypatch.setenv("MRT_WAVEFRONT", "1")
+    acc, st = _gpu_render(scene, w, h, spp)
+    assert st["mode"] == 2
+    _check(acc, ref, meta["rays"], st)
