@@ -89,6 +89,17 @@ enum MrtMatKind {
 };
 #define MRT_MAT_NEEDS_UV 0x100u
 
+/* Scene features (MrtSceneDesc.features): which object classes / materials / textures occur.  The renderer
+   picks a kernel specialised for a superset of this mask. */
+#define MRT_FEAT_TREES 1u      /* bvh_node / pod_bvh trees, triangles */
+#define MRT_FEAT_VOLUMES 2u    /* constant_volume (+ isotropic phase function) */
+#define MRT_FEAT_XFORM 4u      /* translate / rotate_y */
+#define MRT_FEAT_TEX 8u        /* checker / perlin / image textures (and the uv they need) */
+#define MRT_FEAT_METAL 16u
+#define MRT_FEAT_DIELECTRIC 32u
+#define MRT_FEAT_MOVING 64u    /* moving spheres */
+#define MRT_FEAT_ALL 127u
+
 enum MrtTexKind { MRT_X_COLOR = 0, MRT_X_CHECKER = 1, MRT_X_PERLIN = 2, MRT_X_IMAGE = 3 };
 
 /* camera.h:8-14 */
@@ -110,6 +121,8 @@ typedef struct MrtSceneDesc {
     const uint32_t *lights;   /* typed refs (sphere or xz_rect have a pdf; others evaluate to 0) */
     uint32_t sky;             /* 1: sky gradient on miss (sceneSelect < SCENE_CORNELL_BOX, main.cpp:110) */
     uint32_t stack_words;     /* worst-case traversal stack depth in 32-bit words (computed by the flattener) */
+    uint32_t features;        /* MRT_FEAT_* mask of what the scene contains (0 is treated as MRT_FEAT_ALL) */
+    uint32_t reserved0;
     MrtCamera camera;
 
     const MrtF4 *sphere;  uint32_t n_sphere;

@@ -24,7 +24,8 @@ class Camera(C.Structure):
 class SceneDesc(C.Structure):
     _fields_ = [
         ("root", C.c_uint32), ("n_lights", C.c_uint32), ("lights", C.POINTER(C.c_uint32)),
-        ("sky", C.c_uint32), ("stack_words", C.c_uint32), ("camera", Camera),
+        ("sky", C.c_uint32), ("stack_words", C.c_uint32), ("features", C.c_uint32), ("reserved0", C.c_uint32),
+        ("camera", Camera),
         ("sphere", C.POINTER(F4)), ("n_sphere", C.c_uint32),
         ("rect", C.POINTER(F4)), ("n_rect", C.c_uint32),
         ("list", C.POINTER(F4)), ("n_list", C.c_uint32),

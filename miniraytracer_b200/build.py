@@ -18,8 +18,9 @@ LIB = os.path.join(ROOT, "miniraytracer_b200", "libmrt_b200.so")
 EXE = os.path.join(ROOT, "miniraytracer_b200", "mrt_b200")
 
 HOST_SRCS = ["scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "scene_dump.cpp", "flatten.cpp", "host_api.cpp"]
-CUDA_SRCS = ["render_kernel.cu", "render_wavefront.cu"]
-HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
+CUDA_SRCS = ["render_kernel.cu", "render_wavefront.cu", "render_variant_lists.cu", "render_variant_lists_vol.cu",
+             "render_variant_trees.cu", "render_variant_trees_tex.cu", "render_variant_all.cu"]
+HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", "render_kernels.cuh", "render_variants.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
 
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -59,12 +60,18 @@ def build(force=False, verbose=False):
         if force or _stale(o, [s] + hdrs):
             log += _run(["g++"] + CXX_FLAGS + ["-c", s, "-o", o])
         objs.append(o)
+    todo = []
     for src in CUDA_SRCS:
         o = os.path.join(objdir, src + ".o")
         s = os.path.join(CSRC, src)
         if force or _stale(o, [s] + hdrs):
-            log += _run([_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", s, "-o", o])
+            todo.append([_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", s, "-o", o])
         objs.append(o)
+    if todo:   # the kernel variants are independent translation units: compile them in parallel
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            for out in ex.map(_run, todo):
+                log += out
     if force or _stale(LIB, objs):
         log += _run([_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     main_src = os.path.join(CSRC, "main_host.cpp")

@@ -339,6 +339,20 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     d.lights = o.lights.data();
     d.sky = g.sky ? 1u : 0u;
     d.stack_words = fl.depth_w(g.objects) + 2;
+    {   // feature mask: what a specialised kernel must be able to handle
+        uint32_t f = 0;
+        if (!o.node2.empty() || !o.bvh.empty() || !o.trileaf.empty()) f |= MRT_FEAT_TREES;
+        if (!o.vol.empty()) f |= MRT_FEAT_VOLUMES;
+        if (!o.xlate.empty() || !o.rot.empty()) f |= MRT_FEAT_XFORM;
+        for (const Texture &t : g.texs) if (t.kind != TexKind::Color) f |= MRT_FEAT_TEX;
+        for (const Material &m : g.mats) {
+            if (m.kind == MatKind::Metal) f |= MRT_FEAT_METAL;
+            if (m.kind == MatKind::Dielectric) f |= MRT_FEAT_DIELECTRIC;
+            if (m.kind == MatKind::Isotropic) f |= MRT_FEAT_VOLUMES;
+        }
+        for (const Node &n : g.nodes) if (n.kind == NodeKind::Sphere && n.moving) f |= MRT_FEAT_MOVING;
+        d.features = f;
+    }
     const Camera &c = g.camera;
     auto put = [](float *dst, H3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; };
     put(d.camera.origin, c.origin); put(d.camera.u, c.u); put(d.camera.v, c.v); put(d.camera.w, c.w);

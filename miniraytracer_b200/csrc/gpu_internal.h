@@ -31,7 +31,8 @@ struct MrtScene {
     int min_blocks = 0;           // launch-bounds variant (MRT_MINB); 0 = by scene: 5 (96 regs) with BVH trees, else 6 (80 regs)
     uint32_t has_trees = 0;
     uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
-    uint32_t sync_threads = 0;    // block size of the phase-synchronised variant (MRT_SYNC, 0 = off)
+    uint32_t features = 0;        // MRT_FEAT_* mask of the scene -> kernel variant (render_variants.h)
+    int force_all = 0;            // MRT_VARIANT_ALL=1: always use the unspecialised kernels (tuning / A-B)
     cudaStream_t stream = nullptr;
     cudaStream_t poll_stream = nullptr;
     // accumulator

@@ -29,313 +29,10 @@
 #include <vector>
 
 #include "gpu_internal.h"
+#include "render_kernels.cuh"
+#include "render_variants.h"
 
 namespace mrt {
-
-struct RenderArgs {
-    SceneView sc;
-    uint32_t width, height, sqrt_n, s_begin, s_end, max_bounces;
-    uint64_t seed;
-    uint32_t accumulate;
-    uint32_t stack_words;
-    uint32_t n_tasks, pixels_per_task;
-    float4 *acc;
-    unsigned int *ticket;             // global task counter
-    unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
-    const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
-};
-
-constexpr int kWarpsPerBlock = kBlock / 32;
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-
-// One segment of a live path: traverse, shade.  Returns true while the path continues.
-__device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng, Stack &st) {
-    Hit rec;
-    path_advance(a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
-    bool hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
-    return path_shade(a.sc, p, hit, rec, a.max_bounces, rng);
-}
-
-// ------------------------------------------------------------------ mode W
-// Warp task = a chunk of `pixels_per_task` consecutive pixels x all samples of this launch, handed out as
-// one stream of items (pixel-major, sample-minor).  A lane keeps the running sum of the pixel it is
-// working on; when its next item belongs to another pixel it parks that partial sum in its own column of
-// a per-warp shared array part[k][lane] (one writer per element: a lane visits a pixel in one contiguous
-// period because items are handed out in increasing order).  At the end of the chunk every pixel's 32
-// partials are combined by a fixed-order shuffle tree.  The idle tail (lanes waiting for the last paths)
-// is paid once per chunk instead of once per pixel.
-template <int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const RenderArgs a) {
-    extern __shared__ uint32_t smem_stack[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    Stack st;
-    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
-    st.stride = 32u;
-    st.sp = 0;
-    const uint32_t K = a.pixels_per_task;
-    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
-    const uint32_t ns = a.s_end - a.s_begin;
-    unsigned long long rays = 0, nonfinite = 0, iters = 0;
-
-    for (;;) {
-        uint32_t task = 0;
-        if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
-        task = __shfl_sync(0xFFFFFFFFu, task, 0);
-        if (task >= a.n_tasks) break;
-        const uint32_t pix0 = task * K;
-        const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
-        const uint32_t n_items = kp * ns;
-        for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        uint32_t next_i = 0;           // warp-uniform stream cursor
-        uint32_t cur_k = 0xFFFFFFFFu;  // pixel slot of this lane's running sum
-        bool alive = false;
-        Path p;
-        Rng rng;
-        float sr = 0, sg = 0, sb = 0, sc = 0;
-        for (;;) {
-            // regenerate terminated lanes from the stream (warp-converged point)
-            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !alive);
-            if (!alive) {
-                const uint32_t i = next_i + __popc(need & lt_mask);
-                if (i < n_items) {
-                    const uint32_t k = i / ns, s = a.s_begin + (i - k * ns);
-                    if (k != cur_k) {
-                        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
-                        sr = sg = sb = sc = 0;
-                        cur_k = k;
-                    }
-                    const uint32_t pix = pix0 + k;
-                    const uint32_t y = pix / a.width, x = pix - y * a.width;
-                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
-                    alive = true;
-                }
-            }
-            next_i = min(next_i + (uint32_t) __popc(need), n_items);
-            if (!__any_sync(0xFFFFFFFFu, alive)) break;
-            iters++;
-            if (alive) {
-                rays++;
-                if (!path_step(a, p, rng, st)) {
-                    if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
-                    else nonfinite++;
-                    alive = false;
-                }
-            }
-        }
-        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
-        __syncwarp();
-        for (uint32_t k = 0; k < kp; k++) {
-            float4 v = part[k * 32u];
-            v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-            if (lane == 0) {
-                const uint32_t pix = pix0 + k;
-                if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                a.acc[pix] = v;
-            }
-        }
-        __syncwarp();
-    }
-    // statistics: one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
-        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters[0], rays);
-        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
-        atomicAdd(&a.counters[2], nonfinite);
-    }
-}
-
-// --------------------------------------------------------- mode W, phase-synchronised
-// Same stream logic per warp, but the warps of a (large) block run the three phases of an iteration
-// -- advance | intersect | shade -- between block barriers, so that the warps sharing an SM sub-partition
-// execute the same code region at the same time (instruction-cache reuse; ncu round 1: ~40 % of warp stalls
-// were stall_no_inst).  Warps take their tasks independently and keep attending the barriers until every
-// warp of the block has run out of work.
-template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) render_stream_sync(const RenderArgs a) {
-    extern __shared__ uint32_t smem_stack[];
-    constexpr uint32_t kWarps = THREADS / 32;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    Stack st;
-    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
-    st.stride = 32u;
-    st.sp = 0;
-    const uint32_t K = a.pixels_per_task;
-    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarps * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
-    const uint32_t ns = a.s_end - a.s_begin;
-    unsigned long long rays = 0, nonfinite = 0, iters = 0;
-
-    bool warp_done = false, have_task = false, alive = false;
-    uint32_t pix0 = 0, kp = 0, n_items = 0, next_i = 0, cur_k = 0xFFFFFFFFu;
-    Path p;
-    Rng rng;
-    float sr = 0, sg = 0, sb = 0, sc = 0;
-    for (;;) {
-        // ---- warp-level bookkeeping: top up dead lanes, switch chunks, retire
-        while (!warp_done) {
-            if (!have_task) {
-                uint32_t task = 0;
-                if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
-                task = __shfl_sync(0xFFFFFFFFu, task, 0);
-                if (task >= a.n_tasks) { warp_done = true; break; }
-                pix0 = task * K;
-                kp = min(K, n_pixels - pix0);
-                n_items = kp * ns;
-                for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                next_i = 0;
-                cur_k = 0xFFFFFFFFu;
-                sr = sg = sb = sc = 0;
-                have_task = true;
-            }
-            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !alive);
-            if (!alive) {
-                const uint32_t i = next_i + __popc(need & lt_mask);
-                if (i < n_items) {
-                    const uint32_t k = i / ns, s = a.s_begin + (i - k * ns);
-                    if (k != cur_k) {
-                        if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
-                        sr = sg = sb = sc = 0;
-                        cur_k = k;
-                    }
-                    const uint32_t pix = pix0 + k;
-                    const uint32_t y = pix / a.width, x = pix - y * a.width;
-                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
-                    alive = true;
-                }
-            }
-            next_i = min(next_i + (uint32_t) __popc(need), n_items);
-            if (__any_sync(0xFFFFFFFFu, alive)) break;
-            // chunk finished: combine the lanes' partial sums, one writer per pixel
-            if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
-            __syncwarp();
-            for (uint32_t k = 0; k < kp; k++) {
-                float4 v = part[k * 32u];
-                v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-                if (lane == 0) {
-                    const uint32_t pix = pix0 + k;
-                    if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                    a.acc[pix] = v;
-                }
-            }
-            __syncwarp();
-            have_task = false;
-        }
-        if (__syncthreads_and(warp_done ? 1 : 0)) break;
-        if (!warp_done) iters++;
-        // ---- phase B+C
-        if (alive) path_advance(a.sc, p);
-        __syncthreads();
-        // ---- phase D
-        Hit rec;
-        bool hit = false;
-        if (alive) {
-            rays++;
-            hit = intersect(a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
-        }
-        __syncthreads();
-        // ---- phase E
-        if (alive) {
-            if (!path_shade(a.sc, p, hit, rec, a.max_bounces, rng)) {
-                if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
-                else nonfinite++;
-                alive = false;
-            }
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
-        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters[0], rays);
-        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
-        atomicAdd(&a.counters[2], nonfinite);
-    }
-}
-
-// ------------------------------------------------------------------ mode P
-template <int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const RenderArgs a) {
-    extern __shared__ uint32_t smem_stack[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    Stack st;
-    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
-    st.stride = 32u;
-    st.sp = 0;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
-    unsigned long long rays = 0, nonfinite = 0, iters = 0;
-
-    for (;;) {
-        uint32_t task = 0;
-        if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
-        task = __shfl_sync(0xFFFFFFFFu, task, 0);
-        if (task >= a.n_tasks) break;
-        uint32_t next_p = task * a.pixels_per_task;
-        const uint32_t end_p = min(next_p + a.pixels_per_task, n_pixels);
-
-        bool has_pixel = false, alive = false;
-        uint32_t pix = 0, x = 0, y = 0, s = 0;
-        Path p;
-        Rng rng;
-        float sr = 0, sg = 0, sb = 0, sc = 0;
-        for (;;) {
-            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !has_pixel);
-            if (!has_pixel) {
-                const uint32_t cand = next_p + __popc(need & lt_mask);
-                if (cand < end_p) {
-                    pix = cand;
-                    y = pix / a.width; x = pix - y * a.width;
-                    s = a.s_begin;
-                    sr = sg = sb = sc = 0;
-                    has_pixel = true;
-                }
-            }
-            next_p = min(next_p + (uint32_t) __popc(need), end_p);
-            if (!__any_sync(0xFFFFFFFFu, has_pixel)) break;
-            iters++;
-            if (has_pixel) {
-                if (!alive) {
-                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
-                    alive = true;
-                }
-                rays++;
-                if (!path_step(a, p, rng, st)) {
-                    if (path_sample_finite(p)) { sr += p.L.x; sg += p.L.y; sb += p.L.z; sc += 1.0f; }
-                    else nonfinite++;
-                    alive = false;
-                    if (++s == a.s_end) {
-                        float4 v = make_float4(sr, sg, sb, sc);
-                        if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                        a.acc[pix] = v;
-                        has_pixel = false;
-                    }
-                }
-            }
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
-        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters[0], rays);
-        atomicAdd(&a.counters[1], iters);   // warp iterations: rays / (32 * iters) = share of lanes with a live path
-        atomicAdd(&a.counters[2], nonfinite);
-    }
-}
 
 // --------------------------------------------------------------- finalize
 // color = sum / count ; luminance clamp (main.cpp:168-173, vec3.h:275-279)
@@ -495,10 +192,11 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     s->stack_words = d->stack_words ? d->stack_words : 64;
     if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
     if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
-    if (const char *e = getenv("MRT_SYNC")) s->sync_threads = (uint32_t) atoi(e);
     if (const char *e = getenv("MRT_WAVEFRONT")) s->wavefront = atoi(e);
     s->has_volumes = d->n_vol ? 1u : 0u;
     s->has_trees = d->n_node2 ? 1u : 0u;
+    s->features = d->features;
+    if (const char *e = getenv("MRT_VARIANT_ALL")) s->force_all = atoi(e);
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -588,26 +286,12 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.cancel = s->cancel_dev;
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
-    // kernel variant: minimum resident blocks per SM the register allocation is bounded for
-    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 6);   // measured: profiles/r1_notes.md
-    typedef void (*kernel_t)(const RenderArgs);
-    kernel_t kernel = nullptr;
-    uint32_t threads = kBlock;
-    if (mode_w && s->sync_threads) {   // experimental phase-synchronised variants (MRT_SYNC)
-        switch (s->sync_threads) {
-        case 256: threads = 256; kernel = (minb >= 3) ? render_stream_sync<256, 3> : render_stream_sync<256, 2>; break;
-        case 384: threads = 384; kernel = (minb >= 2) ? render_stream_sync<384, 2> : render_stream_sync<384, 1>; break;
-        default: threads = 512; kernel = render_stream_sync<512, 1>; break;
-        }
-    } else {
-        switch (minb) {
-        case 4: kernel = mode_w ? render_pixel_per_warp<4> : render_pixel_per_lane<4>; break;
-        case 6: kernel = mode_w ? render_pixel_per_warp<6> : render_pixel_per_lane<6>; break;
-        case 7: kernel = mode_w ? render_pixel_per_warp<7> : render_pixel_per_lane<7>; break;
-        case 8: kernel = mode_w ? render_pixel_per_warp<8> : render_pixel_per_lane<8>; break;
-        default: minb = 5; kernel = mode_w ? render_pixel_per_warp<5> : render_pixel_per_lane<5>; break;
-        }
-    }
+    // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
+    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 6);
+    if (minb != 5) minb = 6;
+    const Variant *variant = s->force_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
+    const void *kernel = variant->get(mode_w, minb);
+    const uint32_t threads = kBlock;
     const uint32_t warps_per_block = threads / 32u;
     // choose the task size so that every resident warp gets several tasks (load balance) while the idle
     // tail of a task stays small against its body
@@ -645,8 +329,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    kernel<<<grid, threads, smem, s->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    void *kargs[] = {(void *) &a};
+    CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     s->rendered = true;
     s->last = *p;

@@ -1,0 +1,45 @@
+// Kernel variants specialised by scene-feature mask (MRT_FEAT_*).  One translation unit per mask
+// (render_variant_<name>.cu) instantiates the two megakernels of render_kernels.cuh for it; the launcher
+// takes the first variant whose mask covers the scene's.
+#pragma once
+#include <stdint.h>
+
+#include "mrt_types.h"
+
+namespace mrt {
+
+// Cornell-style scenes: lists, rects, spheres, transforms; lambertian / metal / dielectric / light; colour textures
+#define MRT_VARIANT_LISTS (MRT_FEAT_XFORM | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
+// ... plus constant-density volumes
+#define MRT_VARIANT_LISTS_VOL (MRT_VARIANT_LISTS | MRT_FEAT_VOLUMES)
+// tree scenes without transforms, volumes and procedural / image textures (triangle meshes in a Cornell box)
+#define MRT_VARIANT_TREES (MRT_FEAT_TREES | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
+// sphere BVH with procedural textures and motion blur ("In One Weekend")
+#define MRT_VARIANT_TREES_TEX (MRT_VARIANT_TREES | MRT_FEAT_TEX | MRT_FEAT_MOVING)
+
+const void *variant_lists(bool pixel_per_warp, int minb);
+const void *variant_lists_vol(bool pixel_per_warp, int minb);
+const void *variant_trees(bool pixel_per_warp, int minb);
+const void *variant_trees_tex(bool pixel_per_warp, int minb);
+const void *variant_all(bool pixel_per_warp, int minb);
+
+struct Variant {
+    uint32_t mask;
+    const void *(*get)(bool pixel_per_warp, int minb);
+    const char *name;
+};
+inline const Variant *pick_variant(uint32_t scene_features) {
+    static const Variant table[] = {
+        {MRT_VARIANT_LISTS, variant_lists, "lists"},
+        {MRT_VARIANT_LISTS_VOL, variant_lists_vol, "lists+volumes"},
+        {MRT_VARIANT_TREES, variant_trees, "trees"},
+        {MRT_VARIANT_TREES_TEX, variant_trees_tex, "trees+textures"},
+        {MRT_FEAT_ALL, variant_all, "all"},
+    };
+    if (scene_features == 0) scene_features = MRT_FEAT_ALL;   // unknown: keep everything
+    for (const Variant &v : table)
+        if ((scene_features & ~v.mask) == 0) return &v;
+    return &table[4];
+}
+
+}  // namespace mrt

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) wf_logic(const WaveArgs a) {
                     const float4 h1 = a.st.H1[i];
                     rec.p = xyz(h0); rec.n = xyz(h1); rec.u = h1.w; rec.v = a.st.H2[i]; rec.mat = mat; rec.t = 0.f;
                 }
-                if (!path_shade(a.sc, p, hit, rec, a.max_bounces, rng)) {
+                if (!path_shade(MRT_FEAT_ALL, a.sc, p, hit, rec, a.max_bounces, rng)) {
                     if (path_sample_finite(p)) { sum.x += p.L.x; sum.y += p.L.y; sum.z += p.L.z; sum.w += 1.0f; }
                     else dropped++;
                     need_new = true;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) wf_logic(const WaveArgs a) {
                 }
             }
             if (!finished) {
-                path_advance(a.sc, p);
+                path_advance(MRT_FEAT_ALL, a.sc, p);
                 new_rays = 1;
                 live = true;
                 a.st.R0[i] = f4(p.ray.o, p.ray.time);

@@ -35,6 +35,12 @@
 
 namespace mrt {
 
+// Scene-feature specialisation.  Every function below that takes a `feat` argument is force-inlined into a
+// kernel instantiated for a compile-time constant mask (MRT_FEAT_* in mrt_types.h); code for object classes,
+// materials and textures the scene does not contain is removed by constant folding, which shortens the
+// hot loop (fewer branch targets, fewer live registers).  MRT_FEAT_ALL keeps everything.
+#define MRT_HAS(feat, bit) (((feat) & (bit)) != 0u)
+
 #define MRT_PI_F 3.14159265358979323846f /* mrt_math.h:11 */
 
 // ------------------------------------------------------------------ utilities
@@ -273,9 +279,9 @@ MRT_FN void sphere_uv(V3 n, float *u, float *v) {  // sphere.cpp:6-11
     *v = 0.5f + theta * (1.0f / MRT_PI_F);
 }
 // sphere.cpp:13-46.  full=false: only the distance is wanted (volume boundary probe).
-MRT_FN bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+MRT_FN bool hit_sphere(const uint32_t feat, const SceneView &sc, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
     MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
-    V3 cen = sphere_center(s0, s1, sc.sphere, idx, r.time);
+    V3 cen = MRT_HAS(feat, MRT_FEAT_MOVING) ? sphere_center(s0, s1, sc.sphere, idx, r.time) : v3(s0);
     float radius = s0.w;
     V3 oc = r.o - cen;
     float b = dot(oc, r.d);
@@ -296,7 +302,7 @@ MRT_FN bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tm
                 rec.p = ray_eval(r, t);
                 rec.n = (rec.p - cen) / radius;
                 rec.mat = mat;
-                if (f2u(ld4(sc.mat, mat).x) & MRT_MAT_NEEDS_UV) sphere_uv(rec.n, &rec.u, &rec.v);
+                if (MRT_HAS(feat, MRT_FEAT_TEX)) { if (f2u(ld4(sc.mat, mat).x) & MRT_MAT_NEEDS_UV) sphere_uv(rec.n, &rec.u, &rec.v); }
             }
             return true;
         }
@@ -305,7 +311,7 @@ MRT_FN bool hit_sphere(const SceneView &sc, uint32_t idx, const Ray &r, float tm
 }
 
 // rect.cpp:24-45,69-90,130-152.  axis = 0: xy (k=z), 1: xz (k=y), 2: yz (k=x)
-MRT_HD bool hit_rect(const SceneView &sc, uint32_t axis, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
+MRT_HD bool hit_rect(const uint32_t feat, const SceneView &sc, uint32_t axis, uint32_t idx, const Ray &r, float tmin, float tmax, bool full, Hit &rec) {
     MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
     float ok_, dk, oa, da, ob, db;
     if (axis == 0)      { ok_ = r.o.z; dk = r.d.z; oa = r.o.x; da = r.d.x; ob = r.o.y; db = r.d.y; }
@@ -321,7 +327,7 @@ MRT_HD bool hit_rect(const SceneView &sc, uint32_t axis, uint32_t idx, const Ray
     rec.t = t;
     if (full) {
         rec.mat = f2u(q1.z);
-        if (f2u(ld4(sc.mat, rec.mat).x) & MRT_MAT_NEEDS_UV) {
+        if (MRT_HAS(feat, MRT_FEAT_TEX) && (f2u(ld4(sc.mat, rec.mat).x) & MRT_MAT_NEEDS_UV)) {
             rec.u = fdiv(a - q0.x, q0.y - q0.x);
             rec.v = fdiv(b - q0.z, q0.w - q0.z);
         }
@@ -378,11 +384,12 @@ MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float 
 //    (tmin, tmax) and only needs the two distances -> `probe` mode, in which
 //    hits update tmax only and the main record is untouched.  A volume's
 //    boundary must not contain another volume (checked by the flattener).
-MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
+MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
                       Counters *cnt) {
     float tmin = tmin0, tmax = tmax0;
     float main_tmax = tmax0;
-    bool probe = false;
+    bool probe_v = false;
+#define probe (MRT_HAS(feat, MRT_FEAT_VOLUMES) && probe_v)
     float vol_t1 = 0.0f;
     uint32_t cur = sc.root;
     bool ret = false;
@@ -405,7 +412,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 st.push(MRT_FRAME(MRT_F_LIST, f2u(l0.w)));
                 break;   // the LIST frame is popped right away and runs the child loop
             }
-            case MRT_T_BVH: {   // root of a bvh_node / pod_bvh tree: its own box test (scene_object.h:211, triangle.h:175)
+            case MRT_T_BVH: if (!MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {   // root of a bvh_node / pod_bvh tree: its own box test (scene_object.h:211, triangle.h:175)
                 MrtF4 b0 = ld4(sc.bvh, 2 * idx), b1 = ld4(sc.bvh, 2 * idx + 1);
                 if (cnt) cnt->aabb++;
                 ret = false;
@@ -414,7 +421,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 descend = true;
                 break;
             }
-            case MRT_T_NODE2: {
+            case MRT_T_NODE2: if (!MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {
                 // Inner node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
                 // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
                 // (IF_MISS frame).  tmin/tmax are constant inside a tree, so the child box tests made here are
@@ -448,7 +455,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 }
                 break;
             }
-            case MRT_T_TRILEAF: {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
+            case MRT_T_TRILEAF: if (!MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
                 const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
                 ret = false;
                 for (uint32_t i = 0; i < count; i++) {
@@ -461,7 +468,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 break;
             }
             case MRT_T_TRANSLATE:     // scene_object.cpp:9-18
-            case MRT_T_ROTATE_Y: {    // scene_object.cpp:70-98
+            case MRT_T_ROTATE_Y: if (!MRT_HAS(feat, MRT_FEAT_XFORM)) { ret = false; break; } {    // scene_object.cpp:70-98
                 ret = false;
                 MrtF4 r0, r2;
                 if (type == MRT_T_ROTATE_Y) {
@@ -500,12 +507,12 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 descend = true;
                 break;
             }
-            case MRT_T_VOLUME: {      // volumes.cpp:5-36, first probe
+            case MRT_T_VOLUME: if (!MRT_HAS(feat, MRT_FEAT_VOLUMES)) { ret = false; break; } {      // volumes.cpp:5-36, first probe
                 MrtF4 vl = ld4(sc.vol, idx);
                 if (cnt) cnt->vol++;
                 st.push(MRT_FRAME(MRT_F_VOL1, idx));
                 main_tmax = tmax;
-                probe = true;
+                probe_v = true;
                 tmin = -FLT_MAX;
                 tmax = FLT_MAX;
                 cur = f2u(vl.x);
@@ -523,7 +530,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
             if (st.sp == sp0) return ret && !probe;
             uint32_t e = st.pop();
             uint32_t tag = e >> 29;
-            if (tag == MRT_F_IF_MISS) {
+            if (MRT_HAS(feat, MRT_FEAT_TREES) && tag == MRT_F_IF_MISS) {
                 if (ret) continue;
                 cur = e & 0x0FFFFFFFu;
                 break;
@@ -539,10 +546,10 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                     ci++;
                     if (ctype == MRT_T_SPHERE) {
                         if (cnt) cnt->sphere++;
-                        if (hit_sphere(sc, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
+                        if (hit_sphere(feat, sc, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
                     } else if (ctype <= MRT_T_RECT_YZ) {
                         if (cnt) cnt->rect++;
-                        if (hit_rect(sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
+                        if (hit_rect(feat, sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
                     } else {
                         st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
                         cur = c;
@@ -553,7 +560,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 if (composite) break;
                 ret = found;
                 continue;
-            } else if (tag == MRT_F_XLATE_END || tag == MRT_F_ROT_END) {
+            } else if (MRT_HAS(feat, MRT_FEAT_XFORM) && (tag == MRT_F_XLATE_END || tag == MRT_F_ROT_END)) {
                 ray.inside = (int) st.pop();
                 ray.inv.z = st.popf(); ray.inv.y = st.popf(); ray.inv.x = st.popf();
                 ray.d.z = st.popf(); ray.d.y = st.popf(); ray.d.x = st.popf();
@@ -576,10 +583,10 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                     }
                 }
                 continue;
-            } else if (tag == MRT_F_VOL1) {
+            } else if (MRT_HAS(feat, MRT_FEAT_VOLUMES) && tag == MRT_F_VOL1) {
                 uint32_t idx = e & 0x0FFFFFFFu;
                 if (!ret) {
-                    probe = false; tmin = tmin0; tmax = main_tmax;
+                    probe_v = false; tmin = tmin0; tmax = main_tmax;
                     continue;
                 }
                 vol_t1 = tmax;   // rec1.t
@@ -588,11 +595,11 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
                 tmax = FLT_MAX;
                 cur = f2u(ld4(sc.vol, idx).x);
                 break;
-            } else {   // MRT_F_VOL2
+            } else if (MRT_HAS(feat, MRT_FEAT_VOLUMES)) {   // MRT_F_VOL2
                 uint32_t idx = e & 0x0FFFFFFFu;
                 float t2 = tmax;
                 bool both = ret;
-                probe = false; tmin = tmin0; tmax = main_tmax;
+                probe_v = false; tmin = tmin0; tmax = main_tmax;
                 ret = false;
                 if (!both) continue;
                 float t1 = vol_t1;
@@ -616,6 +623,7 @@ MRT_HD bool intersect(const SceneView &sc, Ray &ray, float tmin0, float tmax0, H
         }
     }
 }
+#undef probe
 
 // ------------------------------------------------------------- incremental traversal
 // The same traversal as intersect(), cut into single actions so that a persistent traversal kernel can
@@ -793,10 +801,10 @@ MRT_HD void trav_step(const SceneView &sc, Trav &t, Ray &ray, Hit &rec, Rng &rng
                 ci++;
                 if (ctype == MRT_T_SPHERE) {
                     if (cnt) cnt->sphere++;
-                    if (hit_sphere(sc, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
+                    if (hit_sphere(MRT_FEAT_ALL, sc, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
                 } else if (ctype <= MRT_T_RECT_YZ) {
                     if (cnt) cnt->rect++;
-                    if (hit_rect(sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
+                    if (hit_rect(MRT_FEAT_ALL, sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
                 } else {
                     st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
                     t.cur = c;
@@ -906,11 +914,11 @@ MRT_FN float perlin_turbulence(const SceneView &sc, V3 p) {   // depth 7, textur
     return fabsf(acc);
 }
 
-MRT_FN V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) {
+MRT_FN V3 tex_sample(const uint32_t feat, const SceneView &sc, uint32_t tex, float u, float v, V3 p) {
     for (;;) {
         MrtF4 t = ld4(sc.tex, tex);
         uint32_t kind = f2u(t.x);
-        if (kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);
+        if (!MRT_HAS(feat, MRT_FEAT_TEX) || kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);   // color_tex only
         if (kind == MRT_X_CHECKER) {   // texture.cpp:7-13
             float s = t.w;
             float sines = 1.0f;
@@ -944,7 +952,7 @@ MRT_FN V3 tex_sample(const SceneView &sc, uint32_t tex, float u, float v, V3 p) 
 // object_list::pdf_value / pdf_generate over scene.biased_objects
 // (scene_object.h:64-77); sphere (sphere.cpp:63-79) and xz_rect (rect.cpp:92-107)
 // have pdfs, every other object the base-class defaults (scene_object.h:24-29).
-MRT_FN float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time) {
+MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin, V3 dir, float time) {
     float sum = 0;
     for (uint32_t i = 0; i < sc.n_lights; i++) {
         uint32_t l = ldu(sc.lights, i);
@@ -953,7 +961,7 @@ MRT_FN float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time)
         Hit rec;
         if (type == MRT_T_RECT_XZ) {
             Ray r = make_probe_ray(origin, dir, 0.0f);
-            if (hit_rect(sc, 1, idx, r, 0.001f, FLT_MAX, false, rec)) {
+            if (hit_rect(MRT_FEAT_ALL, sc, 1, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
                 float area = (q0.y - q0.x) * (q0.w - q0.z);
                 float dist_sq = rec.t * rec.t;
@@ -962,7 +970,7 @@ MRT_FN float light_pdf_value(const SceneView &sc, V3 origin, V3 dir, float time)
             }
         } else if (type == MRT_T_SPHERE) {
             Ray r = make_probe_ray(origin, dir, time);
-            if (hit_sphere(sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
+            if (hit_sphere(feat, sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
                 V3 cen = sphere_center(s0, s1, sc.sphere, idx, time);
                 float cos_theta_max = fsqrt(1 - fdiv(s0.w * s0.w, sdot(cen - origin)));
@@ -1067,12 +1075,12 @@ MRT_HD void path_begin(const SceneView &sc, Path &p, Rng &rng, uint32_t x, uint3
 }
 
 // B + C
-MRT_HD void path_advance(const SceneView &sc, Path &p) {
+MRT_HD void path_advance(const uint32_t feat, const SceneView &sc, Path &p) {
     ray_set_dir(p.ray, p.ray.d);
     if (p.pending) {
         const V3 d = p.ray.d;
         float mat_pdf, spdf;
-        if (p.pending == 1) {
+        if (!MRT_HAS(feat, MRT_FEAT_VOLUMES) || p.pending == 1) {   // isotropic only exists as a volume's phase function
             float cosine = dot(d, p.p_n);                    // cosine_pdf::value (pdf.h:24-30); uvw.w == n
             mat_pdf = (cosine > 0) ? fdiv(cosine, MRT_PI_F) : 0.0f;
             spdf = (cosine < 0) ? 0.0f : cosine * (1.0f / MRT_PI_F);   // lambertian::scattering_pdf (material.h:40-46)
@@ -1081,7 +1089,7 @@ MRT_HD void path_advance(const SceneView &sc, Path &p) {
             spdf = 1.0f / (2.0f * MRT_PI_F);                 // isotropic::scattering_pdf (material.h:64-66)
         }
         float pdf_v = mat_pdf;
-        if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(sc, p.ray.o, d, p.ray.time) + mat_pdf);   // mix_pdf::value
+        if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(feat, sc, p.ray.o, d, p.ray.time) + mat_pdf);   // mix_pdf::value
         V3 w = (p.p_att * spdf) / pdf_v;
         p.T = p.T * w;
         p.pending = 0;
@@ -1089,7 +1097,7 @@ MRT_HD void path_advance(const SceneView &sc, Path &p) {
 }
 
 // E: returns true if the path continues (p.ray then holds the next origin and the raw direction)
-MRT_HD bool path_shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
+MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
     if (!hit) {   // main.cpp:108-117
         if (sc.sky) {
             float t = 0.5f * (p.ray.d.y + 1.0f);
@@ -1106,17 +1114,19 @@ MRT_HD bool path_shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, u
     // every other material emits nothing, so hitting the bounce limit ends the path with no contribution
     if (kind == MRT_M_LIGHT ? !(dot(rec.n, r.d) < 0.0f) : !(p.depth < max_bounces)) return false;
     V3 texv = v3(1, 1, 1);
-    if (kind != MRT_M_DIELECTRIC) texv = tex_sample(sc, f2u(m.y), rec.u, rec.v, rec.p);   // albedo / emissive
+    if (!MRT_HAS(feat, MRT_FEAT_DIELECTRIC) || kind != MRT_M_DIELECTRIC) texv = tex_sample(feat, sc, f2u(m.y), rec.u, rec.v, rec.p);   // albedo / emissive
     if (kind == MRT_M_LIGHT) {
         p.L = p.L + p.T * (m.z * texv);
         return false;
     }
     V3 dir;
     int inside = 0;
-    if (kind == MRT_M_METAL || kind == MRT_M_DIELECTRIC) {
+    const bool is_metal = MRT_HAS(feat, MRT_FEAT_METAL) && kind == MRT_M_METAL;
+    const bool is_diel = MRT_HAS(feat, MRT_FEAT_DIELECTRIC) && kind == MRT_M_DIELECTRIC;
+    if (is_metal || is_diel) {
         float dp = 2.0f * dot(r.d, rec.n);          // reflect(), vec3.h:178-181
         dir = r.d - (dp * rec.n);
-        if (kind == MRT_M_METAL) {                  // material.h:84-98
+        if (is_metal) {                             // material.h:84-98
             dir = dir + (1 - m.z) * random_in_sphere(rng);
             p.T = texv * p.T;
         } else {                                    // material.h:106-175
@@ -1148,7 +1158,7 @@ MRT_HD bool path_shade(const SceneView &sc, Path &p, bool hit, const Hit &rec, u
     } else {
         // lambertian (material.h:40-53) / isotropic (material.h:64-73): direction from the mixture pdf
         // (main.cpp:84-92); its weight needs the NORMALISED direction and is applied in path_advance
-        const bool lambert = (kind == MRT_M_LAMBERTIAN);
+        const bool lambert = !MRT_HAS(feat, MRT_FEAT_VOLUMES) || (kind == MRT_M_LAMBERTIAN);
         bool use_light = false;
         if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
         if (use_light) {

@@ -45,13 +45,15 @@ int main(int argc, char **argv) {
     std::string assets = argval(argc, argv, "-assets", "assets");
     const char *out = argval(argc, argv, "-out", nullptr);
     bool want_counters = argflag(argc, argv, "-counters");
-    bool stepper = argflag(argc, argv, "-stepper");   // incremental traversal (trav_step) instead of intersect()
+    bool stepper = argflag(argc, argv, "-stepper");
+    const bool lite = argflag(argc, argv, "-specialised");   // run with the scene's own feature mask instead of MRT_FEAT_ALL   // incremental traversal (trav_step) instead of intersect()
 
     SceneGraph g;
     if (!build_scene(g, scene, float(W) / float(H), assets)) { fprintf(stderr, "scene: %s\n", g.error.c_str()); return 1; }
     FlatScene fs;
     if (!flatten_scene(g, &fs)) { fprintf(stderr, "flatten: %s\n", fs.error.c_str()); return 1; }
     const MrtSceneDesc &d = fs.desc;
+    const uint32_t feat = lite ? (d.features ? d.features : MRT_FEAT_ALL) : MRT_FEAT_ALL;
     SceneView sv;
     sv.sphere = d.sphere; sv.rect = d.rect; sv.list = d.list; sv.bvh = d.bvh; sv.node2 = d.node2; sv.trileaf = d.trileaf; sv.tri = d.tri; sv.trin = d.trin;
     sv.xlate = d.xlate; sv.rot = d.rot; sv.vol = d.vol; sv.mat = d.mat; sv.tex = d.tex; sv.perlin_vec = d.perlin_vec;
@@ -85,7 +87,7 @@ int main(int argc, char **argv) {
                     Path p;
                     path_begin(sv, p, rng, x, y, s, sq, W, H, seed);
                     for (;;) {
-                        path_advance(sv, p);
+                        path_advance(feat, sv, p);
                         cnt.rays++;
                         Hit rec;
                         Stack st;
@@ -97,10 +99,10 @@ int main(int argc, char **argv) {
                             while (trav_active(tr, st)) trav_step(sv, tr, p.ray, rec, rng, st, want_counters ? &cnt : nullptr);
                             hit = trav_hit(tr);
                         } else {
-                            hit = intersect(sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
+                            hit = intersect(feat, sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
                         }
                         if (st.sp != 0) { fprintf(stderr, "stack imbalance\n"); abort(); }
-                        if (!path_shade(sv, p, hit, rec, depth, rng)) break;
+                        if (!path_shade(feat, sv, p, hit, rec, depth, rng)) break;
                     }
                     if (path_sample_finite(p)) {
                         color = color + p.L;

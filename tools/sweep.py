@@ -43,6 +43,7 @@ if __name__ == "__main__":
     ap.add_argument("--sync", default="0")
     ap.add_argument("--wavefront", default="0")
     ap.add_argument("--prefetch", default="0")
+    ap.add_argument("--all", default="0", help="MRT_VARIANT_ALL values")
     args = ap.parse_args()
     for case in args.cases.split(","):
         for minb in args.minb.split(","):
@@ -50,11 +51,11 @@ if __name__ == "__main__":
                 for sync in args.sync.split(","):
                     for wf in args.wavefront.split(","):
                         os.environ["MRT_SYNC"] = sync
-                        for pf in args.prefetch.split(","):
+                        for pf in args.all.split(","):
                             os.environ["MRT_WAVEFRONT"] = wf
-                            os.environ["MRT_PREFETCH"] = pf
+                            os.environ["MRT_VARIANT_ALL"] = pf
                             res = measure(case, int(minb), int(chunk))
                             res["sync"] = int(sync)
                             res["wavefront"] = int(wf)
-                            res["prefetch"] = int(pf)
+                            res["variant_all"] = int(pf)
                             print(json.dumps(res), flush=True)
