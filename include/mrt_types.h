@@ -98,7 +98,8 @@ enum MrtMatKind {
 #define MRT_FEAT_METAL 16u
 #define MRT_FEAT_DIELECTRIC 32u
 #define MRT_FEAT_MOVING 64u    /* moving spheres */
-#define MRT_FEAT_ALL 127u
+#define MRT_FEAT_LIGHT_SPHERE 128u /* the light list holds something other than xz_rects */
+#define MRT_FEAT_ALL 255u
 
 enum MrtTexKind { MRT_X_COLOR = 0, MRT_X_CHECKER = 1, MRT_X_PERLIN = 2, MRT_X_IMAGE = 3 };
 

@@ -351,6 +351,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
             if (m.kind == MatKind::Isotropic) f |= MRT_FEAT_VOLUMES;
         }
         for (const Node &n : g.nodes) if (n.kind == NodeKind::Sphere && n.moving) f |= MRT_FEAT_MOVING;
+        for (uint32_t l : o.lights) if (MRT_REF_TYPE(l) != MRT_T_RECT_XZ) f |= MRT_FEAT_LIGHT_SPHERE;
         d.features = f;
     }
     const Camera &c = g.camera;

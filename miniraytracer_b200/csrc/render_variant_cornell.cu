@@ -1,0 +1,7 @@
+// Megakernel instantiation for the scene-feature mask MRT_VARIANT_CORNELL (see render_variants.h).
+#include "render_kernels.cuh"
+#include "render_variants.h"
+
+namespace mrt {
+const void *variant_cornell(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_CORNELL>(pixel_per_warp, minb); }
+}  // namespace mrt

@@ -8,6 +8,9 @@
 
 namespace mrt {
 
+// exact masks of the two Cornell configurations (no metal; C3 has no dielectric either)
+#define MRT_VARIANT_CORNELL (MRT_FEAT_XFORM | MRT_FEAT_DIELECTRIC)
+#define MRT_VARIANT_CORNELL_VOL (MRT_FEAT_XFORM | MRT_FEAT_VOLUMES)
 // Cornell-style scenes: lists, rects, spheres, transforms; lambertian / metal / dielectric / light; colour textures
 #define MRT_VARIANT_LISTS (MRT_FEAT_XFORM | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
 // ... plus constant-density volumes
@@ -17,6 +20,8 @@ namespace mrt {
 // sphere BVH with procedural textures and motion blur ("In One Weekend")
 #define MRT_VARIANT_TREES_TEX (MRT_VARIANT_TREES | MRT_FEAT_TEX | MRT_FEAT_MOVING)
 
+const void *variant_cornell(bool pixel_per_warp, int minb);
+const void *variant_cornell_vol(bool pixel_per_warp, int minb);
 const void *variant_lists(bool pixel_per_warp, int minb);
 const void *variant_lists_vol(bool pixel_per_warp, int minb);
 const void *variant_trees(bool pixel_per_warp, int minb);
@@ -30,6 +35,8 @@ struct Variant {
 };
 inline const Variant *pick_variant(uint32_t scene_features) {
     static const Variant table[] = {
+        {MRT_VARIANT_CORNELL, variant_cornell, "cornell"},
+        {MRT_VARIANT_CORNELL_VOL, variant_cornell_vol, "cornell+volumes"},
         {MRT_VARIANT_LISTS, variant_lists, "lists"},
         {MRT_VARIANT_LISTS_VOL, variant_lists_vol, "lists+volumes"},
         {MRT_VARIANT_TREES, variant_trees, "trees"},
@@ -39,7 +46,7 @@ inline const Variant *pick_variant(uint32_t scene_features) {
     if (scene_features == 0) scene_features = MRT_FEAT_ALL;   // unknown: keep everything
     for (const Variant &v : table)
         if ((scene_features & ~v.mask) == 0) return &v;
-    return &table[4];
+    return &table[sizeof(table) / sizeof(table[0]) - 1];
 }
 
 }  // namespace mrt

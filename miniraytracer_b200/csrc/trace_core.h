@@ -968,7 +968,7 @@ MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin
                 float cosine = fabsf(dot(dir, v3(0, q1.y, 0)));
                 pv = fdiv(dist_sq, (cosine * area));
             }
-        } else if (type == MRT_T_SPHERE) {
+        } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && type == MRT_T_SPHERE) {
             Ray r = make_probe_ray(origin, dir, time);
             if (hit_sphere(feat, sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
@@ -1005,7 +1005,7 @@ MRT_HD Onb make_onb(V3 n) {
 }
 MRT_HD V3 onb_local(const Onb &o, V3 a) { return (a.x * o.u + a.y * o.v) + a.z * o.w; }
 
-MRT_FN V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rng) {
+MRT_FN V3 light_pdf_generate(const uint32_t feat, const SceneView &sc, V3 origin, float time, Rng &rng) {
     int i = (int) (randf(rng) * (float) sc.n_lights);
     uint32_t l = ldu(sc.lights, (uint32_t) i);
     uint32_t type = MRT_REF_TYPE(l), idx = MRT_REF_INDEX(l);
@@ -1014,7 +1014,7 @@ MRT_FN V3 light_pdf_generate(const SceneView &sc, V3 origin, float time, Rng &rn
         float rx = randf(rng), rz = randf(rng);
         V3 rnd = v3(q0.x + rx * (q0.y - q0.x), q1.x, q0.z + rz * (q0.w - q0.z));
         return rnd - origin;
-    } else if (type == MRT_T_SPHERE) {
+    } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && type == MRT_T_SPHERE) {
         MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
         V3 dir = sphere_center(s0, s1, sc.sphere, idx, time) - origin;
         float dist_sq = sdot(dir);
@@ -1162,7 +1162,7 @@ MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool h
         bool use_light = false;
         if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
         if (use_light) {
-            dir = light_pdf_generate(sc, rec.p, r.time, rng);
+            dir = light_pdf_generate(feat, sc, rec.p, r.time, rng);
         } else if (lambert) {
             Onb uvw = make_onb(rec.n);
             dir = onb_local(uvw, random_cosine_direction(rng));
