@@ -287,8 +287,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
     // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
-    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 6);
-    if (minb != 5) minb = 6;
+    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 8);   // measured: profiles/r1_notes.md
+    if (minb < 5 || minb > 8) minb = 6;
     const Variant *variant = s->force_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
     const void *kernel = variant->get(mode_w, minb);
     const uint32_t threads = kBlock;
@@ -299,25 +299,37 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     size_t smem = 0;
     int blocks_per_sm = 0;
     uint32_t resident_warps = 0;
-    for (int pass = 0; pass < 2; pass++) {
+    auto occupancy = [&](uint32_t k) -> int {
         smem = (size_t) warps_per_block * s->stack_words * 32u * sizeof(uint32_t);
-        if (mode_w) smem += (size_t) warps_per_block * K * 32u * sizeof(float4);
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, (int) threads, smem));
+        if (mode_w) smem += (size_t) warps_per_block * k * 32u * sizeof(float4);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return MRT_E_CUDA; }
+        }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, (int) threads, smem);
+        if (e != cudaSuccess) { set_error(std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e)); return MRT_E_CUDA; }
         if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
         resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * warps_per_block;
-        if (pass == 1) break;
-        if (mode_w) {
-            K = s->chunk_pixels ? s->chunk_pixels : 8u;
-            while (K > 1 && n_pixels / K < 8u * resident_warps) K >>= 1;
-            if (K == 1) break;
-        } else {
-            K = s->chunk_pixels ? s->chunk_pixels : n_pixels / (8u * resident_warps);
-            K = (K + 31u) & ~31u;
-            if (K < 32u) K = 32u;
-            if (K > 1024u) K = 1024u;
-            break;
+        return MRT_OK;
+    };
+    if (mode_w) {
+        // largest chunk (pixels per warp task) that (i) lets the register-limited number of blocks fit in
+        // shared memory and (ii) still leaves every resident warp >= 8 tasks
+        K = s->chunk_pixels ? s->chunk_pixels : 8u;
+        for (;;) {
+            int rc = occupancy(K);
+            if (rc) return rc;
+            if (K == 1 || s->chunk_pixels) break;
+            if (blocks_per_sm >= minb && n_pixels / K >= 8u * resident_warps) break;
+            K >>= 1;
         }
+    } else {
+        int rc = occupancy(0);
+        if (rc) return rc;
+        K = s->chunk_pixels ? s->chunk_pixels : n_pixels / (8u * resident_warps);
+        K = (K + 31u) & ~31u;
+        if (K < 32u) K = 32u;
+        if (K > 1024u) K = 1024u;
     }
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;

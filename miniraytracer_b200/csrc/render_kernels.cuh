@@ -215,6 +215,11 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
 // kernel entry for a feature mask (defined once per render_variant_*.cu)
 template <uint32_t FEAT>
 inline const void *variant_kernel(bool pixel_per_warp, int minb) {
+    // small variants also come with tighter register budgets (7 / 8 resident blocks of 128 threads)
+    if constexpr ((FEAT & (MRT_FEAT_TREES | MRT_FEAT_TEX)) == 0) {
+        if (minb == 7) return pixel_per_warp ? (const void *) render_pixel_per_warp<FEAT, 7> : (const void *) render_pixel_per_lane<FEAT, 7>;
+        if (minb == 8) return pixel_per_warp ? (const void *) render_pixel_per_warp<FEAT, 8> : (const void *) render_pixel_per_lane<FEAT, 8>;
+    }
     if (pixel_per_warp) return (minb == 5) ? (const void *) render_pixel_per_warp<FEAT, 5> : (const void *) render_pixel_per_warp<FEAT, 6>;
     return (minb == 5) ? (const void *) render_pixel_per_lane<FEAT, 5> : (const void *) render_pixel_per_lane<FEAT, 6>;
 }
