@@ -22,7 +22,8 @@ CUDA_SRCS = ["render_kernel.cu", "render_wavefront.cu", "render_variant_cornell.
              "render_variant_trees.cu", "render_variant_trees_tex.cu", "render_variant_all.cu"]
 HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", "render_kernels.cuh", "render_variants.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
 
-NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("MRT_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-I", CSRC, "-I", INC]
 CXX_FLAGS = ["-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", CSRC, "-I", INC]

@@ -58,6 +58,10 @@ struct MrtScene {
     float4 *last_acc = nullptr;
     uint64_t last_rays = 0, last_iters = 0, last_nonfinite = 0;   // filled by the wavefront driver (it is synchronous)
     bool last_wavefront = false;
+    // pixel work order (Z-curve), rebuilt when the frame size changes
+    uint32_t *order_dev = nullptr;
+    uint32_t order_w = 0, order_h = 0;
+    int use_order = 1;            // MRT_ORDER=0: row-major tickets
     // wavefront renderer state (render_wavefront.cu)
     uint32_t has_volumes = 0;
     int wavefront = 0;            // MRT_WAVEFRONT: 1 = use the wavefront renderer

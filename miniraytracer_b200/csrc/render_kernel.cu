@@ -142,6 +142,7 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     mrt_wavefront_free(s);
     for (void *p : s->allocs) cudaFree(p);
     if (s->own_acc) cudaFree(s->own_acc);
+    if (s->order_dev) cudaFree(s->order_dev);
     if (s->final_buf) cudaFree(s->final_buf);
     if (s->argb_buf) cudaFree(s->argb_buf);
     if (s->ticket) cudaFree(s->ticket);
@@ -193,6 +194,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
     if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
     if (const char *e = getenv("MRT_WAVEFRONT")) s->wavefront = atoi(e);
+    if (const char *e = getenv("MRT_ORDER")) s->use_order = atoi(e);
     s->has_volumes = d->n_vol ? 1u : 0u;
     s->has_trees = d->n_node2 ? 1u : 0u;
     s->features = d->features;
@@ -228,6 +230,37 @@ extern "C" int mrt_gpu_bind_accumulator(MrtScene *s, void *device_ptr, uint32_t 
     s->ext_acc = (float4 *) device_ptr;
     s->ext_w = width;
     s->ext_h = height;
+    return MRT_OK;
+}
+
+// Work order of the ticket queue: pixels along a Z-curve (Morton order of (x, y)), so that the warps that are
+// resident at the same time work on a compact block of the image -- their rays visit the same part of the
+// scene, which keeps its nodes in L1/L2 (the reference orders its tiles by an INVERTED Hilbert curve,
+// work_queue.cpp:84-127, to spread the threads; on a GPU locality wins).
+static int ensure_order(MrtScene *s, uint32_t w, uint32_t h) {
+    if (s->order_dev && s->order_w == w && s->order_h == h) return MRT_OK;
+    if (s->order_dev) { cudaFree(s->order_dev); s->order_dev = nullptr; }
+    std::vector<uint32_t> order;
+    order.reserve((size_t) w * h);
+    uint32_t side = 1;
+    while (side < w || side < h) side <<= 1;
+    auto compact = [](uint64_t v) {   // even bits of v
+        v &= 0x5555555555555555ull;
+        v = (v | (v >> 1)) & 0x3333333333333333ull;
+        v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+        v = (v | (v >> 4)) & 0x00FF00FF00FF00FFull;
+        v = (v | (v >> 8)) & 0x0000FFFF0000FFFFull;
+        v = (v | (v >> 16)) & 0x00000000FFFFFFFFull;
+        return (uint32_t) v;
+    };
+    for (uint64_t d = 0; d < (uint64_t) side * side; d++) {
+        uint32_t x = compact(d), y = compact(d >> 1);
+        if (x < w && y < h) order.push_back(y * w + x);
+    }
+    CUDA_TRY(cudaMalloc(&s->order_dev, order.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(s->order_dev, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s->order_w = w;
+    s->order_h = h;
     return MRT_OK;
 }
 
@@ -284,6 +317,12 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.ticket = s->ticket;
     a.counters = s->counters;
     a.cancel = s->cancel_dev;
+    a.order = nullptr;
+    if (s->use_order) {
+        int rc = ensure_order(s, p->width, p->height);
+        if (rc) return rc;
+        a.order = s->order_dev;
+    }
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
     // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)

@@ -26,6 +26,7 @@ struct RenderArgs {
     float4 *acc;
     unsigned int *ticket;             // global task counter
     unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
+    const uint32_t *order;            // work order: item i of the queue is pixel order[i] (Morton tiles), or NULL = row-major
     const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
 };
 
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
                         sr = sg = sb = sc = 0;
                         cur_k = k;
                     }
-                    const uint32_t pix = pix0 + k;
+                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
                     const uint32_t y = pix / a.width, x = pix - y * a.width;
                     path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
                     alive = true;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
             float4 v = part[k * 32u];
             v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
             if (lane == 0) {
-                const uint32_t pix = pix0 + k;
+                const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
                 if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                 a.acc[pix] = v;
             }
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
             if (!has_pixel) {
                 const uint32_t cand = next_p + __popc(need & lt_mask);
                 if (cand < end_p) {
-                    pix = cand;
+                    pix = a.order ? __ldg(a.order + cand) : cand;
                     y = pix / a.width; x = pix - y * a.width;
                     s = a.s_begin;
                     sr = sg = sb = sc = 0;

@@ -12,7 +12,7 @@ from miniraytracer_b200 import api  # noqa: E402
 CASES = {
     "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
     "C3": (6, 960, 540, 1024), "P_C2": (5, 480, 270, 1024), "P_C1": (0, 256, 256, 1024), "P_C4": (7, 480, 270, 256),
-    "P_C5": (8, 480, 270, 256), "Q_C4": (7, 320, 180, 256), "Q_C5": (8, 320, 180, 256), "Q_C1": (0, 200, 200, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
+    "P_C5": (8, 480, 270, 256), "Q_C4": (7, 320, 180, 256), "C4s64": (7, 960, 540, 64), "C4s1k": (7, 960, 540, 1024), "C4s4k": (7, 480, 270, 4096), "C5s1k": (8, 480, 270, 1024), "Q_C5": (8, 320, 180, 256), "Q_C1": (0, 200, 200, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
 }
 
 
@@ -40,22 +40,16 @@ if __name__ == "__main__":
     ap.add_argument("--cases", default="C2")
     ap.add_argument("--minb", default="5")
     ap.add_argument("--chunk", default="0")
-    ap.add_argument("--sync", default="0")
     ap.add_argument("--wavefront", default="0")
-    ap.add_argument("--prefetch", default="0")
     ap.add_argument("--all", default="0", help="MRT_VARIANT_ALL values")
+    ap.add_argument("--order", default="1")
     args = ap.parse_args()
-    for case in args.cases.split(","):
-        for minb in args.minb.split(","):
-            for chunk in args.chunk.split(","):
-                for sync in args.sync.split(","):
-                    for wf in args.wavefront.split(","):
-                        os.environ["MRT_SYNC"] = sync
-                        for pf in args.all.split(","):
-                            os.environ["MRT_WAVEFRONT"] = wf
-                            os.environ["MRT_VARIANT_ALL"] = pf
-                            res = measure(case, int(minb), int(chunk))
-                            res["sync"] = int(sync)
-                            res["wavefront"] = int(wf)
-                            res["variant_all"] = int(pf)
-                            print(json.dumps(res), flush=True)
+    import itertools
+    for case, minb, chunk, wf, pf, order in itertools.product(args.cases.split(","), args.minb.split(","), args.chunk.split(","),
+                                                             args.wavefront.split(","), args.all.split(","), args.order.split(",")):
+        os.environ["MRT_WAVEFRONT"] = wf
+        os.environ["MRT_VARIANT_ALL"] = pf
+        os.environ["MRT_ORDER"] = order
+        res = measure(case, int(minb), int(chunk))
+        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order))
+        print(json.dumps(res), flush=True)
