@@ -61,7 +61,7 @@ struct MrtScene {
     // pixel work order (Z-curve), rebuilt when the frame size changes
     uint32_t *order_dev = nullptr;
     uint32_t order_w = 0, order_h = 0;
-    int use_order = 1;            // MRT_ORDER=0: row-major tickets
+    int use_order = 0;            // MRT_ORDER=1: hand out pixels along a Z-curve (measured: no gain, default off)
     // wavefront renderer state (render_wavefront.cu)
     uint32_t has_volumes = 0;
     int wavefront = 0;            // MRT_WAVEFRONT: 1 = use the wavefront renderer

@@ -352,17 +352,16 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         return MRT_OK;
     };
     if (mode_w) {
-        // largest chunk (pixels per warp task) that (i) lets the register-limited number of blocks fit in
-        // shared memory and (ii) still leaves every resident warp >= 8 tasks
-        K = s->chunk_pixels ? s->chunk_pixels : 8u;
+        // chunk = pixels per warp task.  Measured (profiles/r1_notes.md): 2 pixels beat 8 on every scene -- by
+        // 10 % on the Cornell box and 45 % on the Next-Week scene -- although 8 leaves fewer lanes idle at
+        // chunk ends; with small chunks the lanes of a warp restart together on a fresh pixel every few
+        // hundred samples, which keeps their path depths (and therefore their control flow) aligned.
+        K = s->chunk_pixels ? s->chunk_pixels : 2u;
         for (;;) {
             int rc = occupancy(K);
             if (rc) return rc;
             if (K == 1 || s->chunk_pixels) break;
-            // scenes with trees have working sets of 0.1-2 MB: keep the shared-memory carve-out at the 100 KB
-            // step so that ~128 KB of the SM's 228 KB stay L1 (measured: +50 % on the Next-Week scene)
-            const bool l1_ok = !s->has_trees || (size_t) blocks_per_sm * smem <= 100u * 1024u;
-            if (blocks_per_sm >= minb && l1_ok && n_pixels / K >= 8u * resident_warps) break;
+            if (blocks_per_sm >= minb && n_pixels / K >= 8u * resident_warps) break;
             K >>= 1;
         }
     } else {
