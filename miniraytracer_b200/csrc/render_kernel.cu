@@ -352,16 +352,15 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         return MRT_OK;
     };
     if (mode_w) {
-        // chunk = pixels per warp task.  Measured (profiles/r1_notes.md): 2 pixels beat 8 on every scene -- by
-        // 10 % on the Cornell box and 45 % on the Next-Week scene -- although 8 leaves fewer lanes idle at
-        // chunk ends; with small chunks the lanes of a warp restart together on a fresh pixel every few
-        // hundred samples, which keeps their path depths (and therefore their control flow) aligned.
+        // chunk = pixels per warp task: small, so that the queue holds many short tasks (a task of 8 pixels x
+        // 4096 samples keeps a warp busy for ~0.1 s and the warps that finish early idle at the end of the
+        // launch: measured 2x slower on a 480x270 frame); the idle lanes at chunk ends cost 1-2 %
         K = s->chunk_pixels ? s->chunk_pixels : 2u;
         for (;;) {
             int rc = occupancy(K);
             if (rc) return rc;
             if (K == 1 || s->chunk_pixels) break;
-            if (blocks_per_sm >= minb && n_pixels / K >= 8u * resident_warps) break;
+            if (blocks_per_sm >= minb && n_pixels / K >= 32u * resident_warps) break;
             K >>= 1;
         }
     } else {

@@ -42,14 +42,17 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", default="0")
     ap.add_argument("--wavefront", default="0")
     ap.add_argument("--all", default="0", help="MRT_VARIANT_ALL values")
-    ap.add_argument("--order", default="1")
+    ap.add_argument("--order", default="0")
+    ap.add_argument("--resync", default="0")
     args = ap.parse_args()
     import itertools
     for case, minb, chunk, wf, pf, order in itertools.product(args.cases.split(","), args.minb.split(","), args.chunk.split(","),
                                                              args.wavefront.split(","), args.all.split(","), args.order.split(",")):
+      for resync in args.resync.split(","):
+        os.environ["MRT_RESYNC"] = resync
         os.environ["MRT_WAVEFRONT"] = wf
         os.environ["MRT_VARIANT_ALL"] = pf
         os.environ["MRT_ORDER"] = order
         res = measure(case, int(minb), int(chunk))
-        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order))
+        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order), resync=int(resync))
         print(json.dumps(res), flush=True)
