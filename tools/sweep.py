@@ -12,7 +12,8 @@ from miniraytracer_b200 import api  # noqa: E402
 CASES = {
     "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
     "C3": (6, 960, 540, 1024), "P_C2": (5, 480, 270, 1024), "P_C1": (0, 256, 256, 1024), "P_C4": (7, 480, 270, 256),
-    "P_C5": (8, 480, 270, 256), "Q_C4": (7, 320, 180, 256), "C4s64": (7, 960, 540, 64), "C4s1k": (7, 960, 540, 1024), "C4s4k": (7, 480, 270, 4096), "C5s1k": (8, 480, 270, 1024), "Q_C5": (8, 320, 180, 256), "Q_C1": (0, 200, 200, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
+    "P_C5": (8, 480, 270, 256), "F_C2": (5, 1920, 1080, 256), "F_C3": (6, 1920, 1080, 256), "F_C4": (7, 1920, 1080, 64), "F_C5": (8, 3840, 2160, 36),
+    "Q_C4": (7, 320, 180, 256), "C4s64": (7, 960, 540, 64), "C4s1k": (7, 960, 540, 1024), "C4s4k": (7, 480, 270, 4096), "C5s1k": (8, 480, 270, 1024), "Q_C5": (8, 320, 180, 256), "Q_C1": (0, 200, 200, 256), "P_C1lo": (0, 500, 500, 16), "C4": (7, 960, 540, 256), "C5": (8, 960, 540, 256),
 }
 
 
