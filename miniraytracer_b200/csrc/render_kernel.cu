@@ -355,8 +355,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         // chunk = pixels per warp task: small, so that the queue holds many short tasks (a task of 8 pixels x
         // 4096 samples keeps a warp busy for ~0.1 s and the warps that finish early idle at the end of the
         // launch: measured 2x slower on a 480x270 frame); the idle lanes at chunk ends cost 1-2 %
-        // ... but a chunk should still hold ~2048 items (64 per lane) so that its own idle tail stays small
-        uint32_t k_auto = (2048u + ns - 1u) / ns;
+        // ... but a chunk should still hold ~4096 items (128 per lane) so that its own idle tail stays small
+        uint32_t k_auto = (4096u + ns - 1u) / ns;
         if (k_auto > 8u) k_auto = 8u;
         if (k_auto < 1u) k_auto = 1u;
         K = s->chunk_pixels ? s->chunk_pixels : k_auto;
