@@ -62,6 +62,12 @@ struct MrtScene {
     uint32_t *order_dev = nullptr;
     uint32_t order_w = 0, order_h = 0;
     int use_order = 0;            // MRT_ORDER=1: hand out pixels along a Z-curve (measured: no gain, default off)
+    // binned mode (render_pixel_binned): path pool + classifier boxes of the root list's composite children
+    int binned = 0;               // MRT_BINNED: 0 = off, 1 = pool only (one bin), 2 = + classifier bins
+    uint32_t *pool_dev = nullptr;
+    size_t pool_words = 0;
+    uint32_t n_cls_boxes = 0;
+    float cls_box[3][6];
     // wavefront renderer state (render_wavefront.cu)
     uint32_t has_volumes = 0;
     int wavefront = 0;            // MRT_WAVEFRONT: 1 = use the wavefront renderer

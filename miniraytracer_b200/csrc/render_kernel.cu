@@ -20,7 +20,9 @@
 // are reproducible run to run.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -143,6 +145,7 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     for (void *p : s->allocs) cudaFree(p);
     if (s->own_acc) cudaFree(s->own_acc);
     if (s->order_dev) cudaFree(s->order_dev);
+    if (s->pool_dev) cudaFree(s->pool_dev);
     if (s->final_buf) cudaFree(s->final_buf);
     if (s->argb_buf) cudaFree(s->argb_buf);
     if (s->ticket) cudaFree(s->ticket);
@@ -155,6 +158,104 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
+}
+
+static inline uint32_t bits_of(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+// World-space bounds of a flattened object (host tables).  Only feeds the ray classifier of the binned
+// renderer, which is a grouping heuristic -- so plain float arithmetic, no parity concerns.
+static bool ref_bounds(const MrtSceneDesc *d, uint32_t ref, float lo[3], float hi[3], int depth = 0) {
+    if (depth > 64) return false;
+    const uint32_t type = MRT_REF_TYPE(ref), idx = MRT_REF_INDEX(ref);
+    auto set = [&](const MrtF4 &a, const MrtF4 &b) { lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = b.x; hi[1] = b.y; hi[2] = b.z; };
+    auto merge = [&](const float l2[3], const float h2[3], bool first) {
+        for (int i = 0; i < 3; i++) { lo[i] = first ? l2[i] : std::fmin(lo[i], l2[i]); hi[i] = first ? h2[i] : std::fmax(hi[i], h2[i]); }
+    };
+    switch (type) {
+    case MRT_T_SPHERE: {
+        const MrtF4 &c0 = d->sphere[3 * idx], &c1 = d->sphere[3 * idx + 1];
+        const float r = std::fabs(c0.w);
+        const bool moving = (bits_of(c1.w) >> 31) != 0;
+        for (int i = 0; i < 3; i++) {
+            const float a = (&c0.x)[i], b = moving ? (&c1.x)[i] : a;
+            lo[i] = std::fmin(a, b) - r; hi[i] = std::fmax(a, b) + r;
+        }
+        return true;
+    }
+    case MRT_T_RECT_XY: case MRT_T_RECT_XZ: case MRT_T_RECT_YZ: {
+        const MrtF4 &q0 = d->rect[2 * idx], &q1 = d->rect[2 * idx + 1];
+        const int ka = type == MRT_T_RECT_XY ? 2 : type == MRT_T_RECT_XZ ? 1 : 0;
+        const int aa = type == MRT_T_RECT_YZ ? 1 : 0, ba = type == MRT_T_RECT_XY ? 1 : 2;
+        lo[ka] = q1.x - 1e-4f; hi[ka] = q1.x + 1e-4f;
+        lo[aa] = q0.x; hi[aa] = q0.y; lo[ba] = q0.z; hi[ba] = q0.w;
+        return true;
+    }
+    case MRT_T_LIST: {
+        const MrtF4 &l0 = d->list[2 * idx], &l1 = d->list[2 * idx + 1];
+        if (bits_of(l1.w) >> 31) { set(l0, l1); return true; }
+        bool any = false;
+        for (uint32_t ci = bits_of(l0.w); ci < d->n_child && MRT_REF_TYPE(d->child[ci]) != MRT_T_END; ci++) {
+            float l2[3], h2[3];
+            if (!ref_bounds(d, d->child[ci], l2, h2, depth + 1)) return false;
+            merge(l2, h2, !any);
+            any = true;
+        }
+        return any;
+    }
+    case MRT_T_BVH: set(d->bvh[2 * idx], d->bvh[2 * idx + 1]); return true;
+    case MRT_T_NODE2: {
+        float l2[3] = {d->node2[4 * idx].x, d->node2[4 * idx].y, d->node2[4 * idx].z}, h2[3] = {d->node2[4 * idx + 1].x, d->node2[4 * idx + 1].y, d->node2[4 * idx + 1].z};
+        merge(l2, h2, true);
+        float l3[3] = {d->node2[4 * idx + 2].x, d->node2[4 * idx + 2].y, d->node2[4 * idx + 2].z}, h3[3] = {d->node2[4 * idx + 3].x, d->node2[4 * idx + 3].y, d->node2[4 * idx + 3].z};
+        merge(l3, h3, false);
+        return true;
+    }
+    case MRT_T_TRANSLATE: {
+        const MrtF4 &x = d->xlate[idx];
+        if (!ref_bounds(d, bits_of(x.w), lo, hi, depth + 1)) return false;
+        lo[0] += x.x; lo[1] += x.y; lo[2] += x.z; hi[0] += x.x; hi[1] += x.y; hi[2] += x.z;
+        return true;
+    }
+    case MRT_T_ROTATE_Y: {
+        const MrtF4 &r0 = d->rot[3 * idx], &r1 = d->rot[3 * idx + 1], &r2 = d->rot[3 * idx + 2];
+        if (bits_of(r1.w)) { set(r0, r1); return true; }
+        float l2[3], h2[3];
+        if (!ref_bounds(d, bits_of(r0.w), l2, h2, depth + 1)) return false;
+        bool first = true;
+        for (int c = 0; c < 8; c++) {   // object -> world: x' = cos x + sin z, z' = cos z - sin x (scene_object.cpp:86-93)
+            const float x = (c & 1) ? h2[0] : l2[0], y = (c & 2) ? h2[1] : l2[1], z = (c & 4) ? h2[2] : l2[2];
+            const float pw[3] = {r2.y * x + r2.x * z, y, r2.y * z - r2.x * x};
+            merge(pw, pw, first);
+            first = false;
+        }
+        return true;
+    }
+    case MRT_T_VOLUME: return ref_bounds(d, bits_of(d->vol[idx].x), lo, hi, depth + 1);
+    default: return false;
+    }
+}
+
+// Classifier boxes of the binned renderer: the composite children of the root list (boxes behind transforms,
+// volumes, trees).  Up to kMaxClsBoxes of them, largest first.
+static void find_classifier_boxes(const MrtSceneDesc *d, MrtScene *s) {
+    s->n_cls_boxes = 0;
+    if (MRT_REF_TYPE(d->root) != MRT_T_LIST) return;
+    struct Cand { float vol; float lo[3], hi[3]; };
+    std::vector<Cand> cands;
+    const uint32_t first = bits_of(d->list[2 * MRT_REF_INDEX(d->root)].w);
+    for (uint32_t ci = first; ci < d->n_child && MRT_REF_TYPE(d->child[ci]) != MRT_T_END; ci++) {
+        const uint32_t t = MRT_REF_TYPE(d->child[ci]);
+        if (t <= MRT_T_RECT_YZ) continue;
+        Cand c;
+        if (!ref_bounds(d, d->child[ci], c.lo, c.hi)) continue;
+        c.vol = (c.hi[0] - c.lo[0]) * (c.hi[1] - c.lo[1]) * (c.hi[2] - c.lo[2]);
+        cands.push_back(c);
+    }
+    std::stable_sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.vol > b.vol; });
+    for (size_t i = 0; i < cands.size() && s->n_cls_boxes < kMaxClsBoxes; i++) {
+        float *b = s->cls_box[s->n_cls_boxes++];
+        for (int k = 0; k < 3; k++) { b[k] = cands[i].lo[k]; b[3 + k] = cands[i].hi[k]; }
+    }
 }
 
 extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
@@ -199,6 +300,8 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     s->has_trees = d->n_node2 ? 1u : 0u;
     s->features = d->features;
     if (const char *e = getenv("MRT_VARIANT_ALL")) s->force_all = atoi(e);
+    if (const char *e = getenv("MRT_BINNED")) s->binned = atoi(e);
+    find_classifier_boxes(d, s);
 
     auto cu = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
@@ -329,7 +432,19 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 8);   // measured: profiles/r1_notes.md
     if (minb < 5 || minb > 8) minb = 6;
     const Variant *variant = s->force_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
-    const void *kernel = variant->get(mode_w, minb);
+    const bool binned = mode_w && s->binned > 0;
+    const void *kernel = variant->get(binned ? 2 : (mode_w ? 1 : 0), minb);
+    uint32_t n_bins = 1;
+    a.pool = nullptr;
+    a.n_cls_boxes = 0;
+    a.cls_pending = 0;
+    if (binned && s->binned >= 2) {
+        a.n_cls_boxes = s->n_cls_boxes;
+        a.cls_pending = (s->binned >= 3) ? 1u : 0u;
+        memcpy(a.cls_box, s->cls_box, sizeof(a.cls_box));
+        n_bins = 1u << (a.n_cls_boxes + a.cls_pending);
+    }
+    a.n_bins = n_bins;
     const uint32_t threads = kBlock;
     const uint32_t warps_per_block = threads / 32u;
     // choose the task size so that every resident warp gets several tasks (load balance) while the idle
@@ -341,6 +456,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     auto occupancy = [&](uint32_t k) -> int {
         smem = (size_t) warps_per_block * s->stack_words * 32u * sizeof(uint32_t);
         if (mode_w) smem += (size_t) warps_per_block * k * 32u * sizeof(float4);
+        if (binned) smem += (size_t) warps_per_block * (n_bins + 1u) * kPoolCap;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return MRT_E_CUDA; }
@@ -381,6 +497,15 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     const uint32_t blocks_needed = (a.n_tasks + warps_per_block - 1) / warps_per_block;
     if (grid > blocks_needed) grid = blocks_needed;
 
+    if (binned) {
+        const size_t words = (size_t) grid * warps_per_block * kPoolCap * kStateWords;
+        if (words > s->pool_words) {
+            if (s->pool_dev) { CUDA_TRY(cudaStreamSynchronize(s->stream)); cudaFree(s->pool_dev); s->pool_dev = nullptr; s->pool_words = 0; }
+            CUDA_TRY(cudaMalloc(&s->pool_dev, words * sizeof(uint32_t)));
+            s->pool_words = words;
+        }
+        a.pool = s->pool_dev;
+    }
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
@@ -394,7 +519,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     s->last_grid = grid;
     s->last_block = threads;
     s->last_smem = (uint32_t) smem;
-    s->last_mode = mode_w ? 1u : 0u;
+    s->last_mode = binned ? 3u : (mode_w ? 1u : 0u);
     s->last_acc = acc;
     return MRT_OK;
 }

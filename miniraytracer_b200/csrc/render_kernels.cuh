@@ -16,6 +16,11 @@
 
 namespace mrt {
 
+constexpr uint32_t kPoolCap = 128;     // path slots per warp (slot ids are bytes)
+constexpr uint32_t kStateWords = 21;   // words per parked path, see park_path()
+constexpr uint32_t kMaxClsBoxes = 3;
+constexpr uint32_t kMaxBins = 16;
+
 struct RenderArgs {
     SceneView sc;
     uint32_t width, height, sqrt_n, s_begin, s_end, max_bounces;
@@ -28,6 +33,11 @@ struct RenderArgs {
     unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
     const uint32_t *order;            // work order: item i of the queue is pixel order[i] (Morton tiles), or NULL = row-major
     const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
+    // binned mode (render_pixel_binned): per-warp path pool in global memory (L2 resident) and the ray classifier
+    uint32_t *pool;                   // [warp][kStateWords][kPoolCap]
+    uint32_t n_bins;                  // 1 << (n_cls_boxes + cls_pending)
+    uint32_t n_cls_boxes, cls_pending;
+    float cls_box[kMaxClsBoxes][6];   // world-space boxes (min xyz, max xyz) of the root list's composite children
 };
 
 constexpr int kWarpsPerBlock = kBlock / 32;
@@ -78,6 +88,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
         const uint32_t pix0 = task * K;
         const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
         const uint32_t n_items = kp * ns;
+#pragma unroll 1
         for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         uint32_t next_i = 0;           // warp-uniform stream cursor
@@ -118,6 +129,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
         }
         if (cur_k != 0xFFFFFFFFu) part[cur_k * 32u] = make_float4(sr, sg, sb, sc);
         __syncwarp();
+#pragma unroll 1
         for (uint32_t k = 0; k < kp; k++) {
             float4 v = part[k * 32u];
             v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
@@ -213,16 +225,214 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
     }
 }
 
-// kernel entry for a feature mask (defined once per render_variant_*.cu)
+// ------------------------------------------------------------------ mode B (binned pool)
+// Same warp task as mode W (a chunk of K pixels x all samples of the launch), but the paths of a chunk no
+// longer stay with "their" lane.  Between two segments every live path is parked in a per-warp pool (global
+// memory, L2 resident; 21 words per path) and its slot id is queued in one of n_bins per-warp bins chosen by
+// a cheap classifier of the NEXT ray (which top-level composites its half-line crosses, whether a diffuse
+// weight is pending).  Each iteration the warp
+//   * pops 32 paths from the fullest bin if it holds 32            -> 32 lanes that will do similar things,
+//   * else starts 32 new paths (consecutive samples of a pixel)    -> primary rays, fully coherent,
+//   * else (chunk drained) pops what is left,
+// runs ONE segment for them (path_step, single call site), adds finished paths to the per-lane partial sums
+// part[k][lane] and parks the survivors again.  The schedule depends only on the paths themselves, so the
+// result is reproducible run to run; per-path arithmetic is untouched (same RNG stream, same operations).
+// A live path carries no radiance (only lights and the sky emit, and both end the path), so L is not parked.
+__device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const Path &p, const Rng &rng, uint32_t k) {
+    uint32_t *q = pool + slot;
+    __stcg(q + 0 * kPoolCap, f2u(p.ray.o.x)); __stcg(q + 1 * kPoolCap, f2u(p.ray.o.y)); __stcg(q + 2 * kPoolCap, f2u(p.ray.o.z));
+    __stcg(q + 3 * kPoolCap, f2u(p.ray.d.x)); __stcg(q + 4 * kPoolCap, f2u(p.ray.d.y)); __stcg(q + 5 * kPoolCap, f2u(p.ray.d.z));
+    __stcg(q + 6 * kPoolCap, f2u(p.T.x)); __stcg(q + 7 * kPoolCap, f2u(p.T.y)); __stcg(q + 8 * kPoolCap, f2u(p.T.z));
+    __stcg(q + 9 * kPoolCap, f2u(p.p_att.x)); __stcg(q + 10 * kPoolCap, f2u(p.p_att.y)); __stcg(q + 11 * kPoolCap, f2u(p.p_att.z));
+    __stcg(q + 12 * kPoolCap, f2u(p.p_n.x)); __stcg(q + 13 * kPoolCap, f2u(p.p_n.y)); __stcg(q + 14 * kPoolCap, f2u(p.p_n.z));
+    __stcg(q + 15 * kPoolCap, (uint32_t) rng.state); __stcg(q + 16 * kPoolCap, (uint32_t) (rng.state >> 32));
+    __stcg(q + 17 * kPoolCap, (uint32_t) rng.inc); __stcg(q + 18 * kPoolCap, (uint32_t) (rng.inc >> 32));
+    __stcg(q + 19 * kPoolCap, f2u(p.ray.time));
+    __stcg(q + 20 * kPoolCap, (p.depth & 0xFFFFu) | (p.pending << 16) | ((uint32_t) p.ray.inside << 18) | (k << 28));
+}
+__device__ __forceinline__ void unpark_path(const uint32_t *pool, uint32_t slot, Path &p, Rng &rng, uint32_t &k) {
+    const uint32_t *q = pool + slot;
+    p.ray.o = v3(u2f(__ldcg(q + 0 * kPoolCap)), u2f(__ldcg(q + 1 * kPoolCap)), u2f(__ldcg(q + 2 * kPoolCap)));
+    p.ray.d = v3(u2f(__ldcg(q + 3 * kPoolCap)), u2f(__ldcg(q + 4 * kPoolCap)), u2f(__ldcg(q + 5 * kPoolCap)));
+    p.T = v3(u2f(__ldcg(q + 6 * kPoolCap)), u2f(__ldcg(q + 7 * kPoolCap)), u2f(__ldcg(q + 8 * kPoolCap)));
+    p.p_att = v3(u2f(__ldcg(q + 9 * kPoolCap)), u2f(__ldcg(q + 10 * kPoolCap)), u2f(__ldcg(q + 11 * kPoolCap)));
+    p.p_n = v3(u2f(__ldcg(q + 12 * kPoolCap)), u2f(__ldcg(q + 13 * kPoolCap)), u2f(__ldcg(q + 14 * kPoolCap)));
+    rng.state = (uint64_t) __ldcg(q + 15 * kPoolCap) | ((uint64_t) __ldcg(q + 16 * kPoolCap) << 32);
+    rng.inc = (uint64_t) __ldcg(q + 17 * kPoolCap) | ((uint64_t) __ldcg(q + 18 * kPoolCap) << 32);
+    p.ray.time = u2f(__ldcg(q + 19 * kPoolCap));
+    const uint32_t f = __ldcg(q + 20 * kPoolCap);
+    p.depth = f & 0xFFFFu;
+    p.pending = (f >> 16) & 3u;
+    p.ray.inside = (int) ((f >> 18) & 0x3FFu);
+    k = f >> 28;
+    p.L = v3(0, 0, 0);
+}
+
+// Bin of the path's next ray.  Only a grouping heuristic (every lane still runs the exact algorithm), so
+// fast reciprocals and the un-normalised direction are fine.
+__device__ __forceinline__ uint32_t ray_class(const RenderArgs &a, const Path &p) {
+    uint32_t c = 0;
+    const float ix = __fdividef(1.0f, p.ray.d.x), iy = __fdividef(1.0f, p.ray.d.y), iz = __fdividef(1.0f, p.ray.d.z);
+#pragma unroll 1
+    for (uint32_t j = 0; j < a.n_cls_boxes; j++) {
+        const float *b = a.cls_box[j];
+        float t0 = (b[0] - p.ray.o.x) * ix, t1 = (b[3] - p.ray.o.x) * ix;
+        float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+        t0 = (b[1] - p.ray.o.y) * iy; t1 = (b[4] - p.ray.o.y) * iy;
+        lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+        t0 = (b[2] - p.ray.o.z) * iz; t1 = (b[5] - p.ray.o.z) * iz;
+        lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+        if (hi >= fmaxf(lo, 0.0f)) c |= 1u << j;
+    }
+    if (a.cls_pending && p.pending) c |= 1u << a.n_cls_boxes;
+    return c;
+}
+
+template <uint32_t FEAT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const RenderArgs a) {
+    extern __shared__ uint32_t smem_stack[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Stack st;
+    st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
+    st.stride = 32u;
+    st.sp = 0;
+    const uint32_t K = a.pixels_per_task, NB = a.n_bins;
+    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
+    uint8_t *binq = reinterpret_cast<uint8_t *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u + (size_t) kWarpsPerBlock * K * 32u * 4u)
+                    + (size_t) warp * (NB + 1u) * kPoolCap;
+    uint8_t *freeq = binq + (size_t) NB * kPoolCap;
+    uint32_t *pool = a.pool + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) (kPoolCap * kStateWords);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t ns = a.s_end - a.s_begin;
+    unsigned long long rays = 0, nonfinite = 0, iters = 0;
+
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= a.n_tasks) break;
+        const uint32_t pix0 = task * K;
+        const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
+        const uint32_t n_items = kp * ns;
+#pragma unroll 1
+        for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (uint32_t i = lane; i < kPoolCap; i += 32u) freeq[i] = (uint8_t) i;
+        uint32_t nfree = kPoolCap;   // warp-uniform
+        uint32_t mycnt = 0;          // lane b holds the length of bin b
+        uint32_t next_i = 0;         // warp-uniform stream cursor
+        __syncwarp();
+
+        for (;;) {
+            // fullest bin
+            uint32_t key = (lane < NB) ? ((mycnt << 8) | lane) : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            const uint32_t b = key & 0xFFu, c = key >> 8;
+            uint32_t n;
+            bool gen;
+            if (c >= 32u) { gen = false; n = 32u; }
+            else if (next_i < n_items && nfree >= 32u) { gen = true; n = min(32u, n_items - next_i); }
+            else if (c > 0u) { gen = false; n = c; }
+            else break;
+            const bool active = lane < n;
+            uint32_t slot = 0xFFu, k = 0;
+            Path p;
+            Rng rng;
+            if (gen) {
+                if (active) {
+                    const uint32_t i = next_i + lane;
+                    k = i / ns;
+                    const uint32_t s = a.s_begin + (i - k * ns);
+                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
+                    const uint32_t y = pix / a.width, x = pix - y * a.width;
+                    path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
+                }
+                next_i += n;
+            } else {
+                if (active) {
+                    slot = binq[b * kPoolCap + (c - n) + lane];
+                    unpark_path(pool, slot, p, rng, k);
+                }
+                if (lane == b) mycnt -= n;
+            }
+            iters++;
+            bool cont = false;
+            if (active) {
+                rays++;
+                cont = path_step<FEAT>(a, p, rng, st);
+                if (!cont) {
+                    if (path_sample_finite(p)) {
+                        float4 v = part[k * 32u];
+                        v.x += p.L.x; v.y += p.L.y; v.z += p.L.z; v.w += 1.0f;
+                        part[k * 32u] = v;
+                    } else nonfinite++;
+                }
+            }
+            // slots: finished paths return theirs, new survivors take one (never both in one iteration)
+            const uint32_t m_free = __ballot_sync(0xFFFFFFFFu, active && !cont && slot != 0xFFu);
+            const uint32_t m_alloc = __ballot_sync(0xFFFFFFFFu, cont && slot == 0xFFu);
+            if (m_free) {
+                if ((m_free >> lane) & 1u) freeq[nfree + __popc(m_free & lt_mask)] = (uint8_t) slot;
+                nfree += __popc(m_free);
+            }
+            if (m_alloc) {
+                if ((m_alloc >> lane) & 1u) slot = freeq[nfree - 1u - __popc(m_alloc & lt_mask)];
+                nfree -= __popc(m_alloc);
+            }
+            uint32_t mybin = 0xFFFFFFFFu;
+            if (cont) {
+                mybin = (NB > 1u) ? ray_class(a, p) : 0u;
+                park_path(pool, slot, p, rng, k);
+            }
+#pragma unroll 1
+            for (uint32_t b2 = 0; b2 < NB; b2++) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, mybin == b2);
+                const uint32_t base = __shfl_sync(0xFFFFFFFFu, mycnt, b2);
+                if (mybin == b2) binq[b2 * kPoolCap + base + __popc(m & lt_mask)] = (uint8_t) slot;
+                if (lane == b2) mycnt += __popc(m);
+            }
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (uint32_t k = 0; k < kp; k++) {
+            float4 v = part[k * 32u];
+            v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+            if (lane == 0) {
+                const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
+                if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                a.acc[pix] = v;
+            }
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+        nonfinite += __shfl_xor_sync(0xFFFFFFFFu, nonfinite, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], rays);
+        atomicAdd(&a.counters[1], iters);
+        atomicAdd(&a.counters[2], nonfinite);
+    }
+}
+
+// kernel entry for a feature mask (defined once per render_variant_*.cu); kind: 0 = pixel per lane,
+// 1 = pixel per warp, 2 = pixel per warp with binned path pool
+template <uint32_t FEAT, int MINB>
+inline const void *variant_kernel_minb(int kind) {
+    if (kind == 2) return (const void *) render_pixel_binned<FEAT, MINB>;
+    return kind ? (const void *) render_pixel_per_warp<FEAT, MINB> : (const void *) render_pixel_per_lane<FEAT, MINB>;
+}
 template <uint32_t FEAT>
-inline const void *variant_kernel(bool pixel_per_warp, int minb) {
+inline const void *variant_kernel(int kind, int minb) {
     // small variants also come with tighter register budgets (7 / 8 resident blocks of 128 threads)
     if constexpr ((FEAT & (MRT_FEAT_TREES | MRT_FEAT_TEX)) == 0) {
-        if (minb == 7) return pixel_per_warp ? (const void *) render_pixel_per_warp<FEAT, 7> : (const void *) render_pixel_per_lane<FEAT, 7>;
-        if (minb == 8) return pixel_per_warp ? (const void *) render_pixel_per_warp<FEAT, 8> : (const void *) render_pixel_per_lane<FEAT, 8>;
+        if (minb == 7) return variant_kernel_minb<FEAT, 7>(kind);
+        if (minb == 8) return variant_kernel_minb<FEAT, 8>(kind);
     }
-    if (pixel_per_warp) return (minb == 5) ? (const void *) render_pixel_per_warp<FEAT, 5> : (const void *) render_pixel_per_warp<FEAT, 6>;
-    return (minb == 5) ? (const void *) render_pixel_per_lane<FEAT, 5> : (const void *) render_pixel_per_lane<FEAT, 6>;
+    return (minb == 5) ? variant_kernel_minb<FEAT, 5>(kind) : variant_kernel_minb<FEAT, 6>(kind);
 }
 
 }  // namespace mrt

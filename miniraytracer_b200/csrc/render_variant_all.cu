@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_all(bool pixel_per_warp, int minb) { return variant_kernel<MRT_FEAT_ALL>(pixel_per_warp, minb); }
+const void *variant_all(int kind, int minb) { return variant_kernel<MRT_FEAT_ALL>(kind, minb); }
 }  // namespace mrt

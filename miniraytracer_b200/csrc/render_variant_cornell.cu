@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_cornell(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_CORNELL>(pixel_per_warp, minb); }
+const void *variant_cornell(int kind, int minb) { return variant_kernel<MRT_VARIANT_CORNELL>(kind, minb); }
 }  // namespace mrt

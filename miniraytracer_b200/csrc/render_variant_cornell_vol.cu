@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_cornell_vol(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_CORNELL_VOL>(pixel_per_warp, minb); }
+const void *variant_cornell_vol(int kind, int minb) { return variant_kernel<MRT_VARIANT_CORNELL_VOL>(kind, minb); }
 }  // namespace mrt

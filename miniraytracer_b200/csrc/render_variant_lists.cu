@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_lists(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_LISTS>(pixel_per_warp, minb); }
+const void *variant_lists(int kind, int minb) { return variant_kernel<MRT_VARIANT_LISTS>(kind, minb); }
 }  // namespace mrt

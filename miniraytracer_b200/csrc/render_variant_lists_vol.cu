@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_lists_vol(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_LISTS_VOL>(pixel_per_warp, minb); }
+const void *variant_lists_vol(int kind, int minb) { return variant_kernel<MRT_VARIANT_LISTS_VOL>(kind, minb); }
 }  // namespace mrt

@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_trees(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_TREES>(pixel_per_warp, minb); }
+const void *variant_trees(int kind, int minb) { return variant_kernel<MRT_VARIANT_TREES>(kind, minb); }
 }  // namespace mrt

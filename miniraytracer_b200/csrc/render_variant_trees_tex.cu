@@ -3,5 +3,5 @@
 #include "render_variants.h"
 
 namespace mrt {
-const void *variant_trees_tex(bool pixel_per_warp, int minb) { return variant_kernel<MRT_VARIANT_TREES_TEX>(pixel_per_warp, minb); }
+const void *variant_trees_tex(int kind, int minb) { return variant_kernel<MRT_VARIANT_TREES_TEX>(kind, minb); }
 }  // namespace mrt

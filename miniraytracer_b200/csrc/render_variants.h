@@ -20,17 +20,17 @@ namespace mrt {
 // sphere BVH with procedural textures and motion blur ("In One Weekend")
 #define MRT_VARIANT_TREES_TEX (MRT_VARIANT_TREES | MRT_FEAT_TEX | MRT_FEAT_MOVING)
 
-const void *variant_cornell(bool pixel_per_warp, int minb);
-const void *variant_cornell_vol(bool pixel_per_warp, int minb);
-const void *variant_lists(bool pixel_per_warp, int minb);
-const void *variant_lists_vol(bool pixel_per_warp, int minb);
-const void *variant_trees(bool pixel_per_warp, int minb);
-const void *variant_trees_tex(bool pixel_per_warp, int minb);
-const void *variant_all(bool pixel_per_warp, int minb);
+const void *variant_cornell(int kind, int minb);
+const void *variant_cornell_vol(int kind, int minb);
+const void *variant_lists(int kind, int minb);
+const void *variant_lists_vol(int kind, int minb);
+const void *variant_trees(int kind, int minb);
+const void *variant_trees_tex(int kind, int minb);
+const void *variant_all(int kind, int minb);
 
 struct Variant {
     uint32_t mask;
-    const void *(*get)(bool pixel_per_warp, int minb);
+    const void *(*get)(int kind, int minb);
     const char *name;
 };
 inline const Variant *pick_variant(uint32_t scene_features) {

@@ -72,6 +72,20 @@ MRT_HD float fdiv(float a, float b) {
     return a / b;
 #endif
 }
+MRT_HD float frcp(float x) {   // 1 / x, correctly rounded: the same value as fdiv(1, x) from a shorter sequence
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+// x / len with a shortcut for x == +-0: 0 / len is that same signed zero for any positive finite len, and the
+// zero-numerator case takes the slow path of __fdiv_rn (ncu round 1: 2 slow-path calls per warp iteration in the
+// Cornell box: axis-aligned onb vectors, a light pdf of 0, a scattering pdf of 0).  len_ok = len is positive and finite.
+MRT_HD float fdiv_zero_num(float x, float len, bool len_ok) {
+    if (len_ok && x == 0.0f) return x;
+    return fdiv(x, len);
+}
 MRT_HD bool is_finite(float x) { return (f2u(x) & 0x7F800000u) != 0x7F800000u; }
 
 MRT_HD MrtF4 ld4(const MrtF4 *p, uint32_t i) {
@@ -187,7 +201,7 @@ MRT_HD uint32_t dir_mask(V3 d) {
 }
 MRT_FN void ray_set_dir(Ray &r, V3 dir) {  // direction is normalised by the ctor (ray.h:30)
     r.d = normalize(dir);
-    r.inv = v3(fdiv(1.0f, r.d.x), fdiv(1.0f, r.d.y), fdiv(1.0f, r.d.z));
+    r.inv = v3(frcp(r.d.x), frcp(r.d.y), frcp(r.d.z));
     r.mask = dir_mask(r.d);
 }
 // ray for a primitive self-test (pdf_value): only origin + normalised direction are used
@@ -354,7 +368,7 @@ MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float 
     V3 qvec = cross(tvec, u);
     float vv = dot(r.d, qvec) * sign;
     if ((uu < 0) | (uu > det) | (vv < 0) | ((uu + vv) > det)) return false;
-    float invDet = fdiv(1, det);
+    float invDet = frcp(det);
     float t = dot(v, qvec) * invDet * sign;
     if ((t < tmin) | (t > tmax)) return false;
     rec.t = t;
@@ -609,7 +623,7 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
                 if (t1 < 0) t1 = 0;
                 MrtF4 vl = ld4(sc.vol, idx);
                 float inside_dist = (t2 - t1);
-                float hit_dist = -(fdiv(1, vl.y)) * cr_logf(randf(rng));
+                float hit_dist = -(frcp(vl.y)) * cr_logf(randf(rng));
                 if (hit_dist < inside_dist) {
                     rec.t = t1 + hit_dist;
                     rec.p = ray_eval(ray, rec.t);
@@ -859,7 +873,7 @@ MRT_HD void trav_step(const SceneView &sc, Trav &t, Ray &ray, Hit &rec, Rng &rng
                     if (t1 < 0) t1 = 0;
                     MrtF4 vl = ld4(sc.vol, idx);
                     float inside_dist = (t2 - t1);
-                    float hit_dist = -(fdiv(1, vl.y)) * cr_logf(randf(rng));
+                    float hit_dist = -(frcp(vl.y)) * cr_logf(randf(rng));
                     if (hit_dist < inside_dist) {
                         rec.t = t1 + hit_dist;
                         rec.p = ray_eval(ray, rec.t);
@@ -954,13 +968,17 @@ MRT_FN V3 tex_sample(const uint32_t feat, const SceneView &sc, uint32_t tex, flo
 // have pdfs, every other object the base-class defaults (scene_object.h:24-29).
 MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin, V3 dir, float time) {
     float sum = 0;
+    // every light builds the same probe ray (ray ctor: normalise once more, ray.h:30) -- hoisted out of the loop
+    Ray r = make_probe_ray(origin, dir, time);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
     for (uint32_t i = 0; i < sc.n_lights; i++) {
         uint32_t l = ldu(sc.lights, i);
         uint32_t type = MRT_REF_TYPE(l), idx = MRT_REF_INDEX(l);
         float pv = 0;
         Hit rec;
         if (type == MRT_T_RECT_XZ) {
-            Ray r = make_probe_ray(origin, dir, 0.0f);
             if (hit_rect(MRT_FEAT_ALL, sc, 1, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 q0 = ld4(sc.rect, 2 * idx), q1 = ld4(sc.rect, 2 * idx + 1);
                 float area = (q0.y - q0.x) * (q0.w - q0.z);
@@ -969,29 +987,20 @@ MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin
                 pv = fdiv(dist_sq, (cosine * area));
             }
         } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && type == MRT_T_SPHERE) {
-            Ray r = make_probe_ray(origin, dir, time);
             if (hit_sphere(feat, sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
                 V3 cen = sphere_center(s0, s1, sc.sphere, idx, time);
                 float cos_theta_max = fsqrt(1 - fdiv(s0.w * s0.w, sdot(cen - origin)));
                 float solid_angle = 2 * MRT_PI_F * (1 - cos_theta_max);
-                pv = fdiv(1, solid_angle);
+                pv = frcp(solid_angle);
             }
         }
         sum += pv;
     }
-    return fdiv(sum, (float) sc.n_lights);
+    return fdiv_zero_num(sum, (float) sc.n_lights, true);
 }
 
 struct Onb { V3 u, v, w; };   // onb.h:19-27
-// x / len for the onb construction.  cross(w, a) with an axis vector a always has one component that is
-// exactly +-0 (two for axis-aligned surface normals); 0 / len is that same signed zero for any positive
-// finite len, so the IEEE division -- whose zero-numerator case takes the slow path of __fdiv_rn
-// (ncu round 1: 0.83 slow-path calls per ray in the Cornell box) -- is skipped for it.
-MRT_HD float fdiv_zero_num(float x, float len, bool len_ok) {
-    if (len_ok && x == 0.0f) return x;
-    return fdiv(x, len);
-}
 MRT_HD Onb make_onb(V3 n) {
     Onb o;
     o.w = n;
@@ -1085,12 +1094,14 @@ MRT_HD void path_advance(const uint32_t feat, const SceneView &sc, Path &p) {
             mat_pdf = (cosine > 0) ? fdiv(cosine, MRT_PI_F) : 0.0f;
             spdf = (cosine < 0) ? 0.0f : cosine * (1.0f / MRT_PI_F);   // lambertian::scattering_pdf (material.h:40-46)
         } else {
-            mat_pdf = fdiv(1, (2 * MRT_PI_F));               // isotropic_pdf::value (pdf.h:41-43)
+            mat_pdf = frcp(2 * MRT_PI_F);               // isotropic_pdf::value (pdf.h:41-43)
             spdf = 1.0f / (2.0f * MRT_PI_F);                 // isotropic::scattering_pdf (material.h:64-66)
         }
         float pdf_v = mat_pdf;
         if (sc.n_lights) pdf_v = 0.5f * (light_pdf_value(feat, sc, p.ray.o, d, p.ray.time) + mat_pdf);   // mix_pdf::value
-        V3 w = (p.p_att * spdf) / pdf_v;
+        const V3 num = p.p_att * spdf;
+        const bool pdf_ok = (pdf_v > 0.0f) && (pdf_v < INFINITY);
+        V3 w = v3(fdiv_zero_num(num.x, pdf_v, pdf_ok), fdiv_zero_num(num.y, pdf_v, pdf_ok), fdiv_zero_num(num.z, pdf_v, pdf_ok));
         p.T = p.T * w;
         p.pending = 0;
     }
@@ -1135,7 +1146,7 @@ MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool h
             float ni_over_nt;
             float cosI = -dot(r.d, rec.n);
             if (cosI < 0) { fn = neg(rec.n); ni_over_nt = ref_index; }
-            else          { fn = rec.n;      ni_over_nt = fdiv(1.0f, ref_index); }
+            else          { fn = rec.n;      ni_over_nt = frcp(ref_index); }
             float ncosI = dot(r.d, fn);             // refract(), vec3.h:185-198
             float sinT2 = (ni_over_nt * ni_over_nt) * (1.0f - ncosI * ncosI);
             inside = r.inside;

@@ -177,3 +177,19 @@ def test_wavefront_renderer_parity(scene, w, h, spp, monkeypatch):
     acc, st = _gpu_render(scene, w, h, spp)
     assert st["mode"] == 2
     _check(acc, ref, meta["rays"], st)
+
+
+@needs_ref
+@pytest.mark.parametrize("binned", [1, 2, 3])
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 64), (6, 128, 72, 36), (7, 96, 54, 36), (8, 96, 54, 36), (0, 96, 96, 49)])
+def test_binned_pool_renderer_parity(scene, w, h, spp, binned, monkeypatch):
+    """Mode B (MRT_BINNED: paths parked in a per-warp pool and regrouped by a ray classifier between segments)
+    runs the same per-path arithmetic as the other modes: same ray count, accumulators equal up to the order of
+    the per-pixel sum."""
+    ref, meta = oracle_util.ref_render(scene, w, h, spp)
+    monkeypatch.setenv("MRT_BINNED", str(binned))
+    acc, st = _gpu_render(scene, w, h, spp)
+    assert st["mode"] == 3
+    _check(acc, ref, meta["rays"], st)
+    acc2, _ = _gpu_render(scene, w, h, spp)
+    assert np.array_equal(acc, acc2), "binned schedule must be reproducible run to run"

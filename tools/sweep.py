@@ -17,7 +17,7 @@ CASES = {
 }
 
 
-def measure(case, minb, chunk, reps=2):
+def measure(case, minb, chunk, reps=2, depth=32):
     reps = int(os.environ.get("MRT_SWEEP_REPS", reps))
     scene, w, h, spp = CASES[case]
     os.environ["MRT_MINB"] = str(minb)
@@ -26,7 +26,7 @@ def measure(case, minb, chunk, reps=2):
     r = api.Renderer(hs, 0)
     best = None
     for i in range(reps + 1):
-        r.render_async(w, h, spp)
+        r.render_async(w, h, spp, depth=depth)
         st = r.stats()
         if i > 0 and (best is None or st["kernel_ms"] < best["kernel_ms"]):
             best = st
@@ -44,16 +44,17 @@ if __name__ == "__main__":
     ap.add_argument("--wavefront", default="0")
     ap.add_argument("--all", default="0", help="MRT_VARIANT_ALL values")
     ap.add_argument("--order", default="0")
-    ap.add_argument("--resync", default="0")
+    ap.add_argument("--binned", default="0", help="MRT_BINNED values (0 off, 1 pool, 2 +box bins, 3 +pending bit)")
+    ap.add_argument("--depth", default="32", help="max bounces (comma list)")
     args = ap.parse_args()
     import itertools
     for case, minb, chunk, wf, pf, order in itertools.product(args.cases.split(","), args.minb.split(","), args.chunk.split(","),
                                                              args.wavefront.split(","), args.all.split(","), args.order.split(",")):
-      for resync in args.resync.split(","):
-        os.environ["MRT_RESYNC"] = resync
+      for depth, binned in itertools.product(args.depth.split(","), args.binned.split(",")):
+        os.environ["MRT_BINNED"] = binned
         os.environ["MRT_WAVEFRONT"] = wf
         os.environ["MRT_VARIANT_ALL"] = pf
         os.environ["MRT_ORDER"] = order
-        res = measure(case, int(minb), int(chunk))
-        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order), resync=int(resync))
+        res = measure(case, int(minb), int(chunk), depth=int(depth))
+        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order), depth=int(depth), binned=int(binned))
         print(json.dumps(res), flush=True)
