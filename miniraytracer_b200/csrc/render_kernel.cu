@@ -300,6 +300,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     s->has_trees = d->n_node2 ? 1u : 0u;
     s->features = d->features;
     if (const char *e = getenv("MRT_VARIANT_ALL")) s->force_all = atoi(e);
+    s->binned = 2;   // mode B with classifier bins is the default for >= 32 samples per launch (measured, profiles/r1_notes.md)
     if (const char *e = getenv("MRT_BINNED")) s->binned = atoi(e);
     find_classifier_boxes(d, s);
 
@@ -426,13 +427,15 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         if (rc) return rc;
         a.order = s->order_dev;
     }
+    // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
     const uint32_t ns = p->sample_end - p->sample_begin;
     const bool mode_w = ns >= 32;
-    // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
-    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : 8);   // measured: profiles/r1_notes.md
+    const bool binned = mode_w && s->binned > 0;
+    // measured (profiles/r1_notes.md): tree scenes want 96 registers; list scenes 64 registers / 8 blocks in modes
+    // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)
+    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
     if (minb < 5 || minb > 8) minb = 6;
     const Variant *variant = s->force_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
-    const bool binned = mode_w && s->binned > 0;
     const void *kernel = variant->get(binned ? 2 : (mode_w ? 1 : 0), minb);
     uint32_t n_bins = 1;
     a.pool = nullptr;

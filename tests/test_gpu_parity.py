@@ -71,9 +71,11 @@ def test_config_parity_vs_oracle(name, scene, w, h, spp):
 
 @needs_ref
 @pytest.mark.parametrize("scene,w,h,spp", [(5, 240, 136, 64), (0, 200, 200, 36)])
-def test_pixel_per_warp_mode(scene, w, h, spp):
-    # >= 32 samples per launch selects the pixel-per-warp kernel (lane sums combined by a shuffle tree)
+def test_pixel_per_warp_mode(scene, w, h, spp, monkeypatch):
+    # MRT_BINNED=0 with >= 32 samples per launch selects the plain pixel-per-warp kernel (mode W: lanes keep their
+    # paths, lane sums combined by a shuffle tree); the default for such launches is mode B (test below)
     ref, meta = oracle_util.ref_render(scene, w, h, spp)
+    monkeypatch.setenv("MRT_BINNED", "0")
     acc, st = _gpu_render(scene, w, h, spp)
     assert st["mode"] == 1
     _check(acc, ref, meta["rays"], st)
@@ -180,14 +182,15 @@ def test_wavefront_renderer_parity(scene, w, h, spp, monkeypatch):
 
 
 @needs_ref
-@pytest.mark.parametrize("binned", [1, 2, 3])
+@pytest.mark.parametrize("binned", [None, 1, 2, 3])
 @pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 64), (6, 128, 72, 36), (7, 96, 54, 36), (8, 96, 54, 36), (0, 96, 96, 49)])
 def test_binned_pool_renderer_parity(scene, w, h, spp, binned, monkeypatch):
     """Mode B (MRT_BINNED: paths parked in a per-warp pool and regrouped by a ray classifier between segments)
     runs the same per-path arithmetic as the other modes: same ray count, accumulators equal up to the order of
     the per-pixel sum."""
     ref, meta = oracle_util.ref_render(scene, w, h, spp)
-    monkeypatch.setenv("MRT_BINNED", str(binned))
+    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)   # the default
+    else: monkeypatch.setenv("MRT_BINNED", str(binned))
     acc, st = _gpu_render(scene, w, h, spp)
     assert st["mode"] == 3
     _check(acc, ref, meta["rays"], st)
