@@ -34,7 +34,10 @@
 //   trileaf[2*i]  = first triangle, trileaf[2*i+1] = triangle count      (pod_bvh leaf, triangle.h:179-187)
 //   tri[3*i+0..2] = (m.xyz, bits(mat)), (u.xyz, 0), (v.xyz, 0)         triangle.h:13-22
 //   trin[3*i+0..2]= (mn.xyz,0), (un.xyz,0), (vn.xyz,0)
-//   xlate[i]      = (offset.xyz, bits(child))                          scene_object.h:325-333
+//   xlate[3*i+0]  = (offset.xyz, bits(child))                          scene_object.h:325-333
+//   xlate[3*i+1]  = (cull box min.xyz, bits(hasCullBox))   bounds of the translated object in the parent frame,
+//   xlate[3*i+2]  = (cull box max.xyz, slack)              inflated by slack = 1e-3 x scene scale: a ray that
+//                   misses it skips the node (conservative; the reference tests nothing here)
 //   rot[3*i+0]    = (bbox.min.xyz, bits(child))                        scene_object.h:340-355
 //   rot[3*i+1]    = (bbox.max.xyz, bits(hasBox))
 //   rot[3*i+2]    = (sin_theta, cos_theta, 0, 0)

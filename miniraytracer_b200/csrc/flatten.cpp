@@ -1,6 +1,7 @@
 // Flattener: host scene graph -> the typed structure-of-arrays tables of
 // mrt_types.h.  Topology, child order and the node_order bytes are preserved
 // exactly (the reference's traversal result depends on them).
+#include <cmath>
 #include <cstring>
 #include <map>
 
@@ -10,6 +11,7 @@ namespace mrt {
 
 namespace {
 inline float ubits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t ubits_of(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline MrtF4 f4(float x, float y, float z, float w) { MrtF4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 struct Flattener {
@@ -229,9 +231,15 @@ struct Flattener {
         }
         case NodeKind::Translate: {
             uint32_t c = wrap(node(n.child));
-            uint32_t i = (uint32_t) o.xlate.size();
+            uint32_t i = (uint32_t) o.xlate.size();   // 3 records per translate
             o.xlate.push_back(f4(n.offset.x, n.offset.y, n.offset.z, ubits(c)));
-            ref = MRT_REF(MRT_T_TRANSLATE, i);
+            // cull box: the object's bounds in the parent frame (scene_object.cpp:20-27), inflated after the
+            // whole scene is known (flatten_scene); w of the first record = 1 if there is one
+            Aabb bb;
+            const bool has = g.bounding_box(id, g.camera.time0, g.camera.time1, &bb);
+            o.xlate.push_back(has ? f4(bb.min.x, bb.min.y, bb.min.z, ubits(1u)) : f4(0, 0, 0, ubits(0u)));
+            o.xlate.push_back(has ? f4(bb.max.x, bb.max.y, bb.max.z, 0) : f4(0, 0, 0, 0));
+            ref = MRT_REF(MRT_T_TRANSLATE, i / 3);
             break;
         }
         case NodeKind::RotateY: {
@@ -327,10 +335,29 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     }
     const size_t lim = 0xFFFFFFu;
     if (o.sphere.size() / 3 > lim || o.rect.size() / 2 > lim || o.list.size() / 2 > lim || o.bvh.size() / 2 > lim ||
-        o.node2.size() / 4 > lim || o.trileaf.size() / 2 > lim || o.xlate.size() > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
+        o.node2.size() / 4 > lim || o.trileaf.size() / 2 > lim || o.xlate.size() / 3 > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
         fl.fail("too many objects of one type for a 24-bit index");
     if (o.child.size() > 0x0FFFFFFFu) fl.fail("child table too large");
     if (!fl.ok) return false;
+
+    {   // Inflate the translate cull boxes by 1e-3 of the scene scale: ~1000x the float32 rounding of anything the
+        // exact path computes at these coordinates, so a ray that misses the inflated box cannot be reported as a hit
+        // by the exact transformed-space test (trace_core.h: cull_miss).
+        float scale = 1.0f;
+        auto grow = [&](float v) { v = std::fabs(v); if (v < 1e30f && v > scale) scale = v; };
+        for (size_t i = 0; i < o.sphere.size(); i += 3) { const MrtF4 &a = o.sphere[i], &b = o.sphere[i + 1]; grow(a.x); grow(a.y); grow(a.z); grow(b.x); grow(b.y); grow(b.z); grow(a.w); }
+        for (size_t i = 0; i < o.rect.size(); i += 2) { const MrtF4 &a = o.rect[i]; grow(a.x); grow(a.y); grow(a.z); grow(a.w); grow(o.rect[i + 1].x); }
+        for (size_t i = 0; i < o.bvh.size(); i++) { grow(o.bvh[i].x); grow(o.bvh[i].y); grow(o.bvh[i].z); }
+        for (size_t i = 0; i < o.xlate.size(); i++) { grow(o.xlate[i].x); grow(o.xlate[i].y); grow(o.xlate[i].z); }
+        grow(g.camera.origin.x); grow(g.camera.origin.y); grow(g.camera.origin.z);
+        const float m = 1e-3f * scale;
+        for (size_t i = 0; i < o.xlate.size(); i += 3) {
+            if (!ubits_of(o.xlate[i + 1].w)) continue;
+            o.xlate[i + 1].x -= m; o.xlate[i + 1].y -= m; o.xlate[i + 1].z -= m;
+            o.xlate[i + 2].x += m; o.xlate[i + 2].y += m; o.xlate[i + 2].z += m;
+            o.xlate[i + 2].w = m;
+        }
+    }
 
     MrtSceneDesc &d = o.desc;
     memset(&d, 0, sizeof(d));
@@ -368,7 +395,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out) {
     d.trileaf = o.trileaf.data(); d.n_trileaf = (uint32_t) o.trileaf.size() / 2;
     d.tri = o.tri.data();       d.n_tri = (uint32_t) o.tri.size() / 3;
     d.trin = o.trin.data();
-    d.xlate = o.xlate.data();   d.n_xlate = (uint32_t) o.xlate.size();
+    d.xlate = o.xlate.data();   d.n_xlate = (uint32_t) o.xlate.size() / 3;
     d.rot = o.rot.data();       d.n_rot = (uint32_t) o.rot.size() / 3;
     d.vol = o.vol.data();       d.n_vol = (uint32_t) o.vol.size();
     d.mat = o.mat.data();       d.n_mat = (uint32_t) o.mat.size();

@@ -228,7 +228,7 @@ extern "C" int mrt_scene_load(const char *path, MrtHostScene **out) {
     ok = ok && o.sphere.size() == (size_t) d.n_sphere * 3 && o.rect.size() == (size_t) d.n_rect * 2 && o.list.size() == (size_t) d.n_list * 2 &&
          o.child.size() == d.n_child && o.bvh.size() == (size_t) d.n_bvh * 2 && o.node2.size() == (size_t) d.n_node2 * 4 &&
          o.trileaf.size() == (size_t) d.n_trileaf * 2 && o.tri.size() == (size_t) d.n_tri * 3 && o.trin.size() == o.tri.size() &&
-         o.xlate.size() == d.n_xlate && o.rot.size() == (size_t) d.n_rot * 3 && o.vol.size() == d.n_vol && o.mat.size() == d.n_mat &&
+         o.xlate.size() == (size_t) d.n_xlate * 3 && o.rot.size() == (size_t) d.n_rot * 3 && o.vol.size() == d.n_vol && o.mat.size() == d.n_mat &&
          o.tex.size() == d.n_tex && o.image.size() == d.n_image_bytes && o.lights.size() == d.n_lights;
     if (!ok) { delete s; set_error(std::string("not a valid MRTSCN1 file: ") + path); return MRT_E_SCENE; }
     rebind(o);

@@ -211,7 +211,7 @@ static bool ref_bounds(const MrtSceneDesc *d, uint32_t ref, float lo[3], float h
         return true;
     }
     case MRT_T_TRANSLATE: {
-        const MrtF4 &x = d->xlate[idx];
+        const MrtF4 &x = d->xlate[3 * idx];
         if (!ref_bounds(d, bits_of(x.w), lo, hi, depth + 1)) return false;
         lo[0] += x.x; lo[1] += x.y; lo[2] += x.z; hi[0] += x.x; hi[1] += x.y; hi[2] += x.z;
         return true;
@@ -278,7 +278,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if ((rc = upload(s, d->trileaf, (size_t) d->n_trileaf * 2, &v.trileaf))) return fail(rc);
     if ((rc = upload(s, d->tri, (size_t) d->n_tri * 3, &v.tri))) return fail(rc);
     if ((rc = upload(s, d->trin, (size_t) d->n_tri * 3, &v.trin))) return fail(rc);
-    if ((rc = upload(s, d->xlate, (size_t) d->n_xlate, &v.xlate))) return fail(rc);
+    if ((rc = upload(s, d->xlate, (size_t) d->n_xlate * 3, &v.xlate))) return fail(rc);
     if ((rc = upload(s, d->rot, (size_t) d->n_rot * 3, &v.rot))) return fail(rc);
     if ((rc = upload(s, d->vol, (size_t) d->n_vol, &v.vol))) return fail(rc);
     if ((rc = upload(s, d->mat, (size_t) d->n_mat, &v.mat))) return fail(rc);

@@ -234,6 +234,26 @@ MRT_HD bool aabb_hit(const MrtF4 &bmin, const MrtF4 &bmax, const Ray &r, float t
     return hi > lo;
 }
 
+// Conservative early-out for box-less transform nodes (translate, scene_object.cpp:9-18): true only if the ray
+// certainly misses `lo..hi`, the object's bounds in the parent frame inflated by the flattener by 1e-3 of the scene
+// scale (= slack, ~1000x the float32 rounding of the exact path at scene coordinates).  A miss inside such a node
+// leaves no trace (ray restored, hit record / tmax / RNG untouched), so skipping the node for these rays does
+// not change the result.  Any NaN in the test means "do not skip".
+MRT_HD bool cull_miss(const MrtF4 &lo, const MrtF4 &hi, const Ray &r, float tmin, float tmax) {
+    const float slack = hi.w;
+    float t0 = (lo.x - r.o.x) * r.inv.x, t1 = (hi.x - r.o.x) * r.inv.x;
+    float u0 = (lo.y - r.o.y) * r.inv.y, u1 = (hi.y - r.o.y) * r.inv.y;
+    float v0 = (lo.z - r.o.z) * r.inv.z, v1 = (hi.z - r.o.z) * r.inv.z;
+    // ordered comparisons are false on NaN; "ok" collects that every product is a number
+    const bool ok = (t0 == t0) & (t1 == t1) & (u0 == u0) & (u1 == u1) & (v0 == v0) & (v1 == v1);
+    float nx = t0 < t1 ? t0 : t1, fx = t0 < t1 ? t1 : t0;
+    float ny = u0 < u1 ? u0 : u1, fy = u0 < u1 ? u1 : u0;
+    float nz = v0 < v1 ? v0 : v1, fz = v0 < v1 ? v1 : v0;
+    float enter = nx > ny ? nx : ny; enter = enter > nz ? enter : nz;
+    float leave = fx < fy ? fx : fy; leave = leave < fz ? leave : fz;
+    return ok && ((enter > leave) || (leave < tmin - slack) || (enter > tmax + slack));
+}
+
 // -------------------------------------------------------------- scene (device)
 struct SceneView {
     const MrtF4 *sphere, *rect, *list, *bvh, *node2, *tri, *trin, *xlate, *rot, *vol, *mat, *tex, *perlin_vec;
@@ -494,7 +514,9 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
                     }
                     r2 = ld4(sc.rot, 3 * idx + 2);
                 } else {
-                    r0 = ld4(sc.xlate, idx);
+                    r0 = ld4(sc.xlate, 3 * idx);
+                    MrtF4 c0 = ld4(sc.xlate, 3 * idx + 1);
+                    if (f2u(c0.w) && cull_miss(c0, ld4(sc.xlate, 3 * idx + 2), ray, tmin, tmax)) break;
                     r2 = r0;
                 }
                 if (cnt) cnt->xform++;
@@ -583,7 +605,7 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
                 if (ret && !probe) {
                     uint32_t idx = e & 0x0FFFFFFFu;
                     if (tag == MRT_F_XLATE_END) {
-                        rec.p = rec.p + v3(ld4(sc.xlate, idx));
+                        rec.p = rec.p + v3(ld4(sc.xlate, 3 * idx));
                     } else {
                         MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
                         float sin_t = r2.x, cos_t = r2.y;
@@ -748,7 +770,7 @@ MRT_HD void trav_step(const SceneView &sc, Trav &t, Ray &ray, Hit &rec, Rng &rng
                 }
                 r2 = ld4(sc.rot, 3 * idx + 2);
             } else {
-                r0 = ld4(sc.xlate, idx);
+                r0 = ld4(sc.xlate, 3 * idx);
                 r2 = r0;
             }
             if (cnt) cnt->xform++;
@@ -835,7 +857,7 @@ MRT_HD void trav_step(const SceneView &sc, Trav &t, Ray &ray, Hit &rec, Rng &rng
             if (t.ret && !t.probe) {
                 uint32_t idx = e & 0x0FFFFFFFu;
                 if (tag == MRT_F_XLATE_END) {
-                    rec.p = rec.p + v3(ld4(sc.xlate, idx));
+                    rec.p = rec.p + v3(ld4(sc.xlate, 3 * idx));
                 } else {
                     MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
                     float sin_t = r2.x, cos_t = r2.y;

@@ -81,7 +81,7 @@ def test_scene_file_round_trip(scene, tmp_path):
         return ctypes.string_at(getattr(d, name), count * elem) if count else b""
     for name, count, elem in (("sphere", a.n_sphere * 3, 16), ("rect", a.n_rect * 2, 16), ("list", a.n_list * 2, 16), ("child", a.n_child, 4),
                               ("bvh", a.n_bvh * 2, 16), ("node2", a.n_node2 * 4, 16), ("trileaf", a.n_trileaf * 2, 4), ("tri", a.n_tri * 3, 16),
-                              ("trin", a.n_tri * 3, 16), ("xlate", a.n_xlate, 16), ("rot", a.n_rot * 3, 16), ("vol", a.n_vol, 16),
+                              ("trin", a.n_tri * 3, 16), ("xlate", a.n_xlate * 3, 16), ("rot", a.n_rot * 3, 16), ("vol", a.n_vol, 16),
                               ("mat", a.n_mat, 16), ("tex", a.n_tex, 16), ("lights", a.n_lights, 4), ("image", a.n_image_bytes, 1)):
         assert table(a, name, count, elem) == table(b, name, count, elem), name
     assert ctypes.string_at(ctypes.byref(a.camera), ctypes.sizeof(a.camera)) == ctypes.string_at(ctypes.byref(b.camera), ctypes.sizeof(b.camera))
