@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -90,16 +91,68 @@ __global__ void tonemap_kernel(const float4 *img, uint32_t *argb, uint32_t n, co
 // =========================================================================
 using namespace mrt;
 
-template <typename T>
-static int upload(MrtScene *s, const T *host, size_t count, const T **dev) {
-    *dev = nullptr;
-    if (!host || !count) return MRT_OK;
-    void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
-    s->allocs.push_back(d);
-    CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
-    *dev = (const T *) d;
-    return MRT_OK;
+// Scene tables are packed into ONE device allocation and copied with ONE transfer (a scene is ~20 small tables; a
+// cudaMalloc + cudaMemcpy each cost ~10 ms per upload).  The control block (ticket, counters, ...) lives in the same
+// allocation.
+struct Packer {
+    struct Item { const void *host; size_t bytes; size_t offset; const void **dev; };
+    std::vector<Item> items;
+    size_t total = 0;
+    size_t reserve(size_t bytes) { size_t o = total; total += (bytes + 255u) & ~(size_t) 255u; return o; }
+    template <typename T>
+    void add(const T *host, size_t count, const T **dev) {
+        *dev = nullptr;
+        if (!host || !count) return;
+        Item it{host, count * sizeof(T), 0, (const void **) dev};
+        it.offset = reserve(it.bytes);
+        items.push_back(it);
+    }
+};
+
+// Small pinned words (cancel flag staging, poll results): slots of one process-wide pinned block, because
+// cudaHostAlloc / cudaFreeHost per scene cost milliseconds.
+static std::mutex g_pin_mu;
+static unsigned char *g_pin_block = nullptr;
+static uint64_t g_pin_used = 0;   // bitmap of 64 slots x 64 bytes
+static void *pinned_slot_acquire() {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_block && cudaHostAlloc((void **) &g_pin_block, 64 * 64, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); g_pin_block = nullptr; return nullptr; }
+    for (int i = 0; i < 64; i++)
+        if (!((g_pin_used >> i) & 1u)) { g_pin_used |= (uint64_t) 1 << i; memset(g_pin_block + 64 * i, 0, 64); return g_pin_block + 64 * i; }
+    return nullptr;
+}
+static bool pinned_slot_release(void *p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_block || (unsigned char *) p < g_pin_block || (unsigned char *) p >= g_pin_block + 64 * 64) return false;
+    g_pin_used &= ~((uint64_t) 1 << (((unsigned char *) p - g_pin_block) / 64));
+    return true;
+}
+
+// Path-pool buffers of mode B (tens of MB) are kept in a per-process cache when a scene is destroyed, so that
+// rendering a sequence of scenes / frames does not pay cudaMalloc + cudaFree (an implicit device sync) each time.
+struct PoolBuf { int device; uint32_t *ptr; size_t words; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBuf> g_pool_free;
+static uint32_t *pool_acquire(int device, size_t words, size_t *got_words) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool_free.size(); i++)
+            if (g_pool_free[i].device == device && g_pool_free[i].words >= words) {
+                PoolBuf b = g_pool_free[i];
+                g_pool_free.erase(g_pool_free.begin() + i);
+                *got_words = b.words;
+                return b.ptr;
+            }
+    }
+    uint32_t *p = nullptr;
+    if (cudaMalloc(&p, words * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+    *got_words = words;
+    return p;
+}
+static void pool_release(int device, uint32_t *ptr, size_t words) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_free.size() >= 16) { cudaFree(ptr); return; }
+    g_pool_free.push_back(PoolBuf{device, ptr, words});
 }
 
 extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
@@ -145,15 +198,10 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     for (void *p : s->allocs) cudaFree(p);
     if (s->own_acc) cudaFree(s->own_acc);
     if (s->order_dev) cudaFree(s->order_dev);
-    if (s->pool_dev) cudaFree(s->pool_dev);
+    if (s->pool_dev) pool_release(s->device, s->pool_dev, s->pool_words);
     if (s->final_buf) cudaFree(s->final_buf);
     if (s->argb_buf) cudaFree(s->argb_buf);
-    if (s->ticket) cudaFree(s->ticket);
-    if (s->counters) cudaFree(s->counters);
-    if (s->max_bits) cudaFree(s->max_bits);
-    if (s->cancel_dev) cudaFree(s->cancel_dev);
-    if (s->cancel_pinned) cudaFreeHost(s->cancel_pinned);
-    if (s->poll_host) cudaFreeHost(s->poll_host);
+    if (s->poll_host && !pinned_slot_release(s->poll_host)) cudaFreeHost(s->poll_host);   // control words live in the scene allocation
     if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -269,24 +317,39 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     SceneView &v = s->view;
     memset(&v, 0, sizeof(v));
-    if ((rc = upload(s, d->sphere, (size_t) d->n_sphere * 3, &v.sphere))) return fail(rc);
-    if ((rc = upload(s, d->rect, (size_t) d->n_rect * 2, &v.rect))) return fail(rc);
-    if ((rc = upload(s, d->list, (size_t) d->n_list * 2, &v.list))) return fail(rc);
-    if ((rc = upload(s, d->child, (size_t) d->n_child, &v.child))) return fail(rc);
-    if ((rc = upload(s, d->bvh, (size_t) d->n_bvh * 2, &v.bvh))) return fail(rc);
-    if ((rc = upload(s, d->node2, (size_t) d->n_node2 * 4, &v.node2))) return fail(rc);
-    if ((rc = upload(s, d->trileaf, (size_t) d->n_trileaf * 2, &v.trileaf))) return fail(rc);
-    if ((rc = upload(s, d->tri, (size_t) d->n_tri * 3, &v.tri))) return fail(rc);
-    if ((rc = upload(s, d->trin, (size_t) d->n_tri * 3, &v.trin))) return fail(rc);
-    if ((rc = upload(s, d->xlate, (size_t) d->n_xlate * 3, &v.xlate))) return fail(rc);
-    if ((rc = upload(s, d->rot, (size_t) d->n_rot * 3, &v.rot))) return fail(rc);
-    if ((rc = upload(s, d->vol, (size_t) d->n_vol, &v.vol))) return fail(rc);
-    if ((rc = upload(s, d->mat, (size_t) d->n_mat, &v.mat))) return fail(rc);
-    if ((rc = upload(s, d->tex, (size_t) d->n_tex, &v.tex))) return fail(rc);
-    if ((rc = upload(s, d->perlin_vec, d->perlin_vec ? 256 : 0, &v.perlin_vec))) return fail(rc);
-    if ((rc = upload(s, d->perlin_perm, d->perlin_perm ? 768 : 0, &v.perlin_perm))) return fail(rc);
-    if ((rc = upload(s, d->image, (size_t) d->n_image_bytes, &v.image))) return fail(rc);
-    if ((rc = upload(s, d->lights, (size_t) d->n_lights, &v.lights))) return fail(rc);
+    Packer pk;
+    pk.add(d->sphere, (size_t) d->n_sphere * 3, &v.sphere);
+    pk.add(d->rect, (size_t) d->n_rect * 2, &v.rect);
+    pk.add(d->list, (size_t) d->n_list * 2, &v.list);
+    pk.add(d->child, (size_t) d->n_child, &v.child);
+    pk.add(d->bvh, (size_t) d->n_bvh * 2, &v.bvh);
+    pk.add(d->node2, (size_t) d->n_node2 * 4, &v.node2);
+    pk.add(d->trileaf, (size_t) d->n_trileaf * 2, &v.trileaf);
+    pk.add(d->tri, (size_t) d->n_tri * 3, &v.tri);
+    pk.add(d->trin, (size_t) d->n_tri * 3, &v.trin);
+    pk.add(d->xlate, (size_t) d->n_xlate * 3, &v.xlate);
+    pk.add(d->rot, (size_t) d->n_rot * 3, &v.rot);
+    pk.add(d->vol, (size_t) d->n_vol, &v.vol);
+    pk.add(d->mat, (size_t) d->n_mat, &v.mat);
+    pk.add(d->tex, (size_t) d->n_tex, &v.tex);
+    pk.add(d->perlin_vec, d->perlin_vec ? 256 : 0, &v.perlin_vec);
+    pk.add(d->perlin_perm, d->perlin_perm ? 768 : 0, &v.perlin_perm);
+    pk.add(d->image, (size_t) d->n_image_bytes, &v.image);
+    pk.add(d->lights, (size_t) d->n_lights, &v.lights);
+    const size_t ctrl_off = pk.reserve(256);   // ticket | counters[4] | max_bits | cancel, zero-initialised
+    {
+        std::vector<unsigned char> staging(pk.total, 0);
+        for (const Packer::Item &it : pk.items) memcpy(staging.data() + it.offset, it.host, it.bytes);
+        unsigned char *base = nullptr;
+        if (cudaMalloc((void **) &base, pk.total) != cudaSuccess) { set_error(std::string("cudaMalloc scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
+        s->allocs.push_back(base);
+        if (cudaMemcpy(base, staging.data(), pk.total, cudaMemcpyHostToDevice) != cudaSuccess) { set_error(std::string("cudaMemcpy scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
+        for (const Packer::Item &it : pk.items) *it.dev = base + it.offset;
+        s->counters = (unsigned long long *) (base + ctrl_off);          // 32 bytes
+        s->ticket = (unsigned int *) (base + ctrl_off + 64);
+        s->max_bits = (unsigned int *) (base + ctrl_off + 128);
+        s->cancel_dev = (int *) (base + ctrl_off + 192);
+    }
     v.root = d->root;
     v.n_lights = d->n_lights;
     v.sky = d->sky;
@@ -308,13 +371,15 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
         if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return false; }
         return true;
     };
-    if (!cu(cudaMalloc(&s->ticket, sizeof(unsigned int)), "cudaMalloc ticket")) return fail(MRT_E_CUDA);
-    if (!cu(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long)), "cudaMalloc counters")) return fail(MRT_E_CUDA);
-    if (!cu(cudaMalloc(&s->max_bits, sizeof(unsigned int)), "cudaMalloc max_bits")) return fail(MRT_E_CUDA);
-    if (!cu(cudaMalloc(&s->cancel_dev, sizeof(int)), "cudaMalloc cancel")) return fail(MRT_E_CUDA);
-    if (!cu(cudaMemset(s->cancel_dev, 0, sizeof(int)), "cudaMemset cancel")) return fail(MRT_E_CUDA);
-    if (!cu(cudaHostAlloc(&s->cancel_pinned, sizeof(int), cudaHostAllocDefault), "cudaHostAlloc cancel")) return fail(MRT_E_CUDA);
-    if (!cu(cudaHostAlloc(&s->poll_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc poll")) return fail(MRT_E_CUDA);
+    {   // pinned words: poll_host[0..1] and the cancel staging word share one 64-byte slot
+        void *slot = pinned_slot_acquire();
+        if (!slot) {
+            if (!cu(cudaHostAlloc(&slot, 64, cudaHostAllocDefault), "cudaHostAlloc control words")) return fail(MRT_E_CUDA);
+            memset(slot, 0, 64);
+        }
+        s->poll_host = (unsigned long long *) slot;
+        s->cancel_pinned = (int *) ((unsigned char *) slot + 32);
+    }
     if (!cu(cudaStreamCreateWithFlags(&s->poll_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(MRT_E_CUDA);
     if (!cu(cudaEventCreate(&s->ev0), "cudaEventCreate")) return fail(MRT_E_CUDA);
     if (!cu(cudaEventCreate(&s->ev1), "cudaEventCreate")) return fail(MRT_E_CUDA);
@@ -503,9 +568,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     if (binned) {
         const size_t words = (size_t) grid * warps_per_block * kPoolCap * kStateWords;
         if (words > s->pool_words) {
-            if (s->pool_dev) { CUDA_TRY(cudaStreamSynchronize(s->stream)); cudaFree(s->pool_dev); s->pool_dev = nullptr; s->pool_words = 0; }
-            CUDA_TRY(cudaMalloc(&s->pool_dev, words * sizeof(uint32_t)));
-            s->pool_words = words;
+            if (s->pool_dev) { CUDA_TRY(cudaStreamSynchronize(s->stream)); pool_release(s->device, s->pool_dev, s->pool_words); s->pool_dev = nullptr; s->pool_words = 0; }
+            s->pool_dev = pool_acquire(s->device, words, &s->pool_words);
+            if (!s->pool_dev) { set_error(std::string("cudaMalloc path pool: ") + cudaGetErrorString(cudaGetLastError())); return MRT_E_CUDA; }
         }
         a.pool = s->pool_dev;
     }
