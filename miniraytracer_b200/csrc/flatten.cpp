@@ -2,6 +2,7 @@
 // mrt_types.h.  Topology, child order and the node_order bytes are preserved
 // exactly (the reference's traversal result depends on them).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -236,7 +237,8 @@ struct Flattener {
             // cull box: the object's bounds in the parent frame (scene_object.cpp:20-27), inflated after the
             // whole scene is known (flatten_scene); w of the first record = 1 if there is one
             Aabb bb;
-            const bool has = g.bounding_box(id, g.camera.time0, g.camera.time1, &bb);
+            static const bool no_cull = getenv("MRT_NO_CULL") != nullptr;   // A/B switch for the parity test of the cull
+            const bool has = !no_cull && g.bounding_box(id, g.camera.time0, g.camera.time1, &bb);
             o.xlate.push_back(has ? f4(bb.min.x, bb.min.y, bb.min.z, ubits(1u)) : f4(0, 0, 0, ubits(0u)));
             o.xlate.push_back(has ? f4(bb.max.x, bb.max.y, bb.max.z, 0) : f4(0, 0, 0, 0));
             ref = MRT_REF(MRT_T_TRANSLATE, i / 3);

@@ -67,14 +67,15 @@ def build_emul():
     return exe
 
 
-def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0):
+def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, env=None):
     from miniraytracer_b200.accfile import read_acc
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         path = f.name
     try:
         r = subprocess.run([exe, "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(spp),
                             "-depth", str(depth), "-seed", str(seed), "-s0", str(s0), "-s1", str(s1), "-assets", ASSETS,
-                            "-out", path, "-counters"], check=True, capture_output=True, text=True)
+                            "-out", path, "-counters"], check=True, capture_output=True, text=True,
+                           env=dict(os.environ, **env) if env else None)
         acc, meta = read_acc(path)
         meta["counters"] = json.loads(r.stdout.strip().splitlines()[-1])
         return acc, meta

@@ -52,3 +52,15 @@ def test_depth_limit_and_seed(emul_bin):
         assert meta["rays"] == rmeta["rays"]
         res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
         assert res["n_bad"] == 0, res
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 16), (6, 160, 90, 16), (7, 128, 72, 9)])
+def test_translate_cull_box_is_conservative(emul_bin, scene, w, h, spp):
+    """The flattener gives every translate node an inflated parent-frame box and the traversal skips the node for
+    rays that miss it (trace_core.h: cull_miss).  The reference tests nothing there, so the cull must never change a
+    result: with and without it the accumulators are bit-identical, and fewer transforms are entered."""
+    a, ma = oracle_util.emul_render(emul_bin, scene, w, h, spp)
+    b, mb = oracle_util.emul_render(emul_bin, scene, w, h, spp, env={"MRT_NO_CULL": "1"})
+    assert ma["rays"] == mb["rays"]
+    np.testing.assert_array_equal(a, b)
+    assert ma["counters"]["xform"] < mb["counters"]["xform"]
