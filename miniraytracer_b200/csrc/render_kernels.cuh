@@ -331,13 +331,29 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
             const uint32_t b = key & 0xFFu, c = key >> 8;
             uint32_t n;
-            bool gen;
+            bool gen, drain = false;
             if (c >= 32u) { gen = false; n = 32u; }
             else if (next_i < n_items && nfree >= 32u) { gen = true; n = min(32u, n_items - next_i); }
-            else if (c > 0u) { gen = false; n = c; }
+            else if (c > 0u) { gen = false; drain = true; n = c; }
             else break;
-            const bool active = lane < n;
             uint32_t slot = 0xFFu, k = 0;
+            // Tree scenes have up to 8 bins and low-spp chunks: draining them one partial bin at a time left 14-20 %
+            // of the lanes without a path (C4/C5).  List scenes (2-4 bins) lose 2 % to it instead -> compile-time.
+            constexpr bool kMultiDrain = (FEAT & MRT_FEAT_TREES) != 0;
+            if (kMultiDrain && drain && NB > 1u) {
+                // no bin holds a full warp and there is nothing left to start (end of the chunk, or the pool is
+                // full): fill the 32 lanes from several bins, in bin order
+                n = 0;
+#pragma unroll 1
+                for (uint32_t b2 = 0; b2 < NB && n < 32u; b2++) {
+                    const uint32_t cb = __shfl_sync(0xFFFFFFFFu, mycnt, b2);
+                    const uint32_t take = min(cb, 32u - n);
+                    if (lane >= n && lane < n + take) slot = binq[b2 * kPoolCap + (cb - take) + (lane - n)];
+                    if (lane == b2) mycnt -= take;
+                    n += take;
+                }
+            }
+            const bool active = lane < n;
             Path p;
             Rng rng;
             if (gen) {
@@ -351,11 +367,11 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
                 }
                 next_i += n;
             } else {
-                if (active) {
-                    slot = binq[b * kPoolCap + (c - n) + lane];
-                    unpark_path(pool, slot, p, rng, k);
+                if (!(kMultiDrain && drain && NB > 1u)) {
+                    if (active) slot = binq[b * kPoolCap + (c - n) + lane];
+                    if (lane == b) mycnt -= n;
                 }
-                if (lane == b) mycnt -= n;
+                if (active) unpark_path(pool, slot, p, rng, k);
             }
             iters++;
             bool cont = false;
