@@ -66,6 +66,8 @@ struct MrtScene {
     int binned = 0;               // MRT_BINNED: 0 = off, 1 = pool only (one bin), 2 = + classifier bins
     uint32_t *pool_dev = nullptr;
     size_t pool_words = 0;
+    uint32_t *stage_dev = nullptr;   // finished samples of the chunks in flight (float4 per path)
+    size_t stage_words = 0;
     uint32_t n_cls_boxes = 0;
     float cls_box[3][6];
     // wavefront renderer state (render_wavefront.cu)

@@ -199,6 +199,7 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (s->own_acc) cudaFree(s->own_acc);
     if (s->order_dev) cudaFree(s->order_dev);
     if (s->pool_dev) pool_release(s->device, s->pool_dev, s->pool_words);
+    if (s->stage_dev) pool_release(s->device, s->stage_dev, s->stage_words);
     if (s->final_buf) cudaFree(s->final_buf);
     if (s->argb_buf) cudaFree(s->argb_buf);
     if (s->poll_host && !pinned_slot_release(s->poll_host)) cudaFreeHost(s->poll_host);   // control words live in the scene allocation
@@ -494,8 +495,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     }
     // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
     const uint32_t ns = p->sample_end - p->sample_begin;
-    const bool mode_w = ns >= 32;
-    const bool binned = mode_w && s->binned > 0;
+    const bool binned = s->binned > 0 && ns <= kMaxStageItems;   // mode B takes any sample count that fits its staging array
+    const bool mode_w = binned || ns >= 32;
     // measured (profiles/r1_notes.md): tree scenes want 96 registers; list scenes 64 registers / 8 blocks in modes
     // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)
     int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
@@ -504,6 +505,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     const void *kernel = variant->get(binned ? 2 : (mode_w ? 1 : 0), minb);
     uint32_t n_bins = 1;
     a.pool = nullptr;
+    a.stage = nullptr;
+    a.stage_items = 0;
     a.n_cls_boxes = 0;
     a.cls_pending = 0;
     if (binned && s->binned >= 2) {
@@ -523,7 +526,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     uint32_t resident_warps = 0;
     auto occupancy = [&](uint32_t k) -> int {
         smem = (size_t) warps_per_block * s->stack_words * 32u * sizeof(uint32_t);
-        if (mode_w) smem += (size_t) warps_per_block * k * 32u * sizeof(float4);
+        if (mode_w && !binned) smem += (size_t) warps_per_block * k * 32u * sizeof(float4);
         if (binned) smem += (size_t) warps_per_block * (n_bins + 1u) * kPoolCap;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -535,7 +538,21 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * warps_per_block;
         return MRT_OK;
     };
-    if (mode_w) {
+    if (binned) {
+        // chunk = warp task: ~4096 paths whatever the samples per pixel (the sums live in a staging array in global
+        // memory, not in shared memory), but at least 32 tasks per resident warp on small frames, at least 256 paths
+        int rc = occupancy(0);
+        if (rc) return rc;
+        const uint64_t total = (uint64_t) n_pixels * ns;
+        uint64_t target = total / ((uint64_t) resident_warps * 32u);   // >= 32 tasks per resident warp: load balance at the end of the launch
+        if (target > 4096u) target = 4096u;
+        if (target < 256u) target = 256u;
+        K = (uint32_t) (target / ns);
+        if (s->chunk_pixels) K = s->chunk_pixels;
+        if (K < 1u) K = 1u;
+        if ((uint64_t) K * ns > kMaxStageItems) K = kMaxStageItems / ns;
+        if (K > n_pixels) K = n_pixels;
+    } else if (mode_w) {
         // chunk = pixels per warp task: small, so that the queue holds many short tasks (a task of 8 pixels x
         // 4096 samples keeps a warp busy for ~0.1 s and the warps that finish early idle at the end of the
         // launch: measured 2x slower on a 480x270 frame); the idle lanes at chunk ends cost 1-2 %
@@ -573,6 +590,14 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
             if (!s->pool_dev) { set_error(std::string("cudaMalloc path pool: ") + cudaGetErrorString(cudaGetLastError())); return MRT_E_CUDA; }
         }
         a.pool = s->pool_dev;
+        a.stage_items = K * ns;
+        const size_t swords = (size_t) grid * warps_per_block * a.stage_items * 4u;
+        if (swords > s->stage_words) {
+            if (s->stage_dev) { CUDA_TRY(cudaStreamSynchronize(s->stream)); pool_release(s->device, s->stage_dev, s->stage_words); s->stage_dev = nullptr; s->stage_words = 0; }
+            s->stage_dev = pool_acquire(s->device, swords, &s->stage_words);
+            if (!s->stage_dev) { set_error(std::string("cudaMalloc sample staging: ") + cudaGetErrorString(cudaGetLastError())); return MRT_E_CUDA; }
+        }
+        a.stage = reinterpret_cast<float4 *>(s->stage_dev);
     }
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));

@@ -20,6 +20,7 @@ constexpr uint32_t kPoolCap = 128;     // path slots per warp (slot ids are byte
 constexpr uint32_t kStateWords = 21;   // words per parked path, see park_path()
 constexpr uint32_t kMaxClsBoxes = 3;
 constexpr uint32_t kMaxBins = 16;
+constexpr uint32_t kMaxStageItems = 8192;   // item index has 14 bits in the parked state
 
 struct RenderArgs {
     SceneView sc;
@@ -35,6 +36,8 @@ struct RenderArgs {
     const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
     // binned mode (render_pixel_binned): per-warp path pool in global memory (L2 resident) and the ray classifier
     uint32_t *pool;                   // [warp][kStateWords][kPoolCap]
+    float4 *stage;                    // [warp][stage_items]: finished samples of the warp's current chunk, by item index
+    uint32_t stage_items;             // pixels_per_task * samples of this launch (<= kMaxStageItems)
     uint32_t n_bins;                  // 1 << (n_cls_boxes + cls_pending)
     uint32_t n_cls_boxes, cls_pending;
     float cls_box[kMaxClsBoxes][6];   // world-space boxes (min xyz, max xyz) of the root list's composite children
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
 // part[k][lane] and parks the survivors again.  The schedule depends only on the paths themselves, so the
 // result is reproducible run to run; per-path arithmetic is untouched (same RNG stream, same operations).
 // A live path carries no radiance (only lights and the sky emit, and both end the path), so L is not parked.
-__device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const Path &p, const Rng &rng, uint32_t k) {
+__device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const Path &p, const Rng &rng, uint32_t item) {
     uint32_t *q = pool + slot;
     __stcg(q + 0 * kPoolCap, f2u(p.ray.o.x)); __stcg(q + 1 * kPoolCap, f2u(p.ray.o.y)); __stcg(q + 2 * kPoolCap, f2u(p.ray.o.z));
     __stcg(q + 3 * kPoolCap, f2u(p.ray.d.x)); __stcg(q + 4 * kPoolCap, f2u(p.ray.d.y)); __stcg(q + 5 * kPoolCap, f2u(p.ray.d.z));
@@ -248,9 +251,9 @@ __device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const P
     __stcg(q + 15 * kPoolCap, (uint32_t) rng.state); __stcg(q + 16 * kPoolCap, (uint32_t) (rng.state >> 32));
     __stcg(q + 17 * kPoolCap, (uint32_t) rng.inc); __stcg(q + 18 * kPoolCap, (uint32_t) (rng.inc >> 32));
     __stcg(q + 19 * kPoolCap, f2u(p.ray.time));
-    __stcg(q + 20 * kPoolCap, (p.depth & 0xFFFFu) | (p.pending << 16) | ((uint32_t) p.ray.inside << 18) | (k << 28));
+    __stcg(q + 20 * kPoolCap, (p.depth & 0xFFu) | (p.pending << 8) | (((uint32_t) p.ray.inside & 0xFFu) << 10) | (item << 18));
 }
-__device__ __forceinline__ void unpark_path(const uint32_t *pool, uint32_t slot, Path &p, Rng &rng, uint32_t &k) {
+__device__ __forceinline__ void unpark_path(const uint32_t *pool, uint32_t slot, Path &p, Rng &rng, uint32_t &item) {
     const uint32_t *q = pool + slot;
     p.ray.o = v3(u2f(__ldcg(q + 0 * kPoolCap)), u2f(__ldcg(q + 1 * kPoolCap)), u2f(__ldcg(q + 2 * kPoolCap)));
     p.ray.d = v3(u2f(__ldcg(q + 3 * kPoolCap)), u2f(__ldcg(q + 4 * kPoolCap)), u2f(__ldcg(q + 5 * kPoolCap)));
@@ -261,10 +264,10 @@ __device__ __forceinline__ void unpark_path(const uint32_t *pool, uint32_t slot,
     rng.inc = (uint64_t) __ldcg(q + 17 * kPoolCap) | ((uint64_t) __ldcg(q + 18 * kPoolCap) << 32);
     p.ray.time = u2f(__ldcg(q + 19 * kPoolCap));
     const uint32_t f = __ldcg(q + 20 * kPoolCap);
-    p.depth = f & 0xFFFFu;
-    p.pending = (f >> 16) & 3u;
-    p.ray.inside = (int) ((f >> 18) & 0x3FFu);
-    k = f >> 28;
+    p.depth = f & 0xFFu;
+    p.pending = (f >> 8) & 3u;
+    p.ray.inside = (int) ((f >> 10) & 0xFFu);
+    item = f >> 18;
     p.L = v3(0, 0, 0);
 }
 
@@ -297,11 +300,13 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     st.stride = 32u;
     st.sp = 0;
     const uint32_t K = a.pixels_per_task, NB = a.n_bins;
-    float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
-    uint8_t *binq = reinterpret_cast<uint8_t *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u + (size_t) kWarpsPerBlock * K * 32u * 4u)
-                    + (size_t) warp * (NB + 1u) * kPoolCap;
+    uint8_t *binq = reinterpret_cast<uint8_t *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * (NB + 1u) * kPoolCap;
     uint8_t *freeq = binq + (size_t) NB * kPoolCap;
     uint32_t *pool = a.pool + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) (kPoolCap * kStateWords);
+    // finished samples go to a per-warp staging array indexed by item (global memory, written once, read once) and
+    // are summed per pixel at the end of the chunk in ITEM order -- so the result does not depend on which lane ran
+    // which path, the chunk size does not depend on the samples per pixel, and no shared memory is needed for sums
+    float4 *stage = a.stage + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) a.stage_items;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_pixels = a.width * a.height;
     const uint32_t ns = a.s_end - a.s_begin;
@@ -315,8 +320,6 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         const uint32_t pix0 = task * K;
         const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
         const uint32_t n_items = kp * ns;
-#pragma unroll 1
-        for (uint32_t k = 0; k < kp; k++) part[k * 32u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (uint32_t i = lane; i < kPoolCap; i += 32u) freeq[i] = (uint8_t) i;
         uint32_t nfree = kPoolCap;   // warp-uniform
@@ -358,10 +361,10 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             Rng rng;
             if (gen) {
                 if (active) {
-                    const uint32_t i = next_i + lane;
-                    k = i / ns;
-                    const uint32_t s = a.s_begin + (i - k * ns);
-                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
+                    k = next_i + lane;   // item index within the chunk
+                    const uint32_t kk = k / ns;
+                    const uint32_t s = a.s_begin + (k - kk * ns);
+                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + kk) : pix0 + kk;
                     const uint32_t y = pix / a.width, x = pix - y * a.width;
                     path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
                 }
@@ -379,11 +382,9 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
                 rays++;
                 cont = path_step<FEAT>(a, p, rng, st);
                 if (!cont) {
-                    if (path_sample_finite(p)) {
-                        float4 v = part[k * 32u];
-                        v.x += p.L.x; v.y += p.L.y; v.z += p.L.z; v.w += 1.0f;
-                        part[k * 32u] = v;
-                    } else nonfinite++;
+                    const bool fin = path_sample_finite(p);
+                    __stcs(stage + k, fin ? make_float4(p.L.x, p.L.y, p.L.z, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f));
+                    if (!fin) nonfinite++;
                 }
             }
             // slots: finished paths return theirs, new survivors take one (never both in one iteration)
@@ -411,9 +412,27 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             }
             __syncwarp();
         }
+        __syncwarp();
+        __threadfence_block();   // this warp's staged samples (written by other lanes) are visible to every lane
 #pragma unroll 1
         for (uint32_t k = 0; k < kp; k++) {
-            float4 v = part[k * 32u];
+            // samples k*ns .. k*ns+ns-1 of pixel k: lane l adds items l, l+32, ... in order, then a fixed shuffle tree
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *src = stage + k * ns;
+            uint32_t i = lane;
+#pragma unroll 1
+            for (; i + 7u * 32u < ns; i += 8u * 32u) {   // eight loads in flight, added in item order
+                float4 q[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) q[j] = __ldcs(src + i + 32u * j);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { v.x += q[j].x; v.y += q[j].y; v.z += q[j].z; v.w += q[j].w; }
+            }
+#pragma unroll 1
+            for (; i < ns; i += 32u) {
+                const float4 q = __ldcs(src + i);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
             v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
             if (lane == 0) {
                 const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;

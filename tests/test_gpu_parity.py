@@ -81,15 +81,19 @@ def test_pixel_per_warp_mode(scene, w, h, spp, monkeypatch):
     _check(acc, ref, meta["rays"], st)
 
 
-def test_modes_and_slices_agree():
-    # 64 spp in one launch (pixel-per-warp) == four accumulated 16-sample slices (pixel-per-lane)
+@pytest.mark.parametrize("binned,slice_mode", [("0", 0), (None, 3)])
+def test_modes_and_slices_agree(binned, slice_mode, monkeypatch):
+    # 64 spp in one launch == four accumulated 16-sample slices; with MRT_BINNED=0 the slices run the pixel-per-lane
+    # kernel (mode P), by default mode B takes any sample count
+    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)
+    else: monkeypatch.setenv("MRT_BINNED", binned)
     w, h, spp = 160, 90, 64
     full, st = _gpu_render(5, w, h, spp)
     hs = api.HostScene(5, w, h)
     r = api.Renderer(hs, 0)
     for i in range(4):
         r.render_async(w, h, spp, sample_begin=16 * i, sample_end=16 * (i + 1), accumulate=(i > 0))
-        assert r.stats()["mode"] == 0
+        assert r.stats()["mode"] == slice_mode
     parts = r.readback()
     r.close(); hs.close()
     np.testing.assert_array_equal(parts[..., 3], full[..., 3])
@@ -224,3 +228,19 @@ def test_progressive_passes_single_gpu():
     np.testing.assert_array_equal(got[..., 3], full[..., 3])
     res = accfile.compare(accfile.finalize(got), accfile.finalize(full), rel=1e-5)
     assert res["n_bad"] == 0, res
+
+
+def test_binned_result_does_not_depend_on_the_schedule(monkeypatch):
+    """Mode B sums the finished samples of a pixel in item order from its staging array, so the accumulator is
+    bit-identical whatever the bins, the chunk size or the launch bounds (i.e. whichever lane ran which path)."""
+    ref = None
+    for env in ({"MRT_BINNED": "1"}, {"MRT_BINNED": "2"}, {"MRT_BINNED": "3"}, {"MRT_BINNED": "2", "MRT_CHUNK": "3"},
+                {"MRT_BINNED": "2", "MRT_MINB": "8"}):
+        for k in ("MRT_BINNED", "MRT_CHUNK", "MRT_MINB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        acc, st = _gpu_render(6, 128, 72, 64)
+        assert st["mode"] == 3
+        if ref is None: ref = acc
+        else: np.testing.assert_array_equal(acc, ref)
