@@ -39,11 +39,11 @@ WORKLOAD_DESC = {
     "C5": "triangle meshes (bunny + teapot) 3840x2160, 4096 spp, 32 bounces",
 }
 FP32_LANES_PER_SM = 128
-# From the ncu --set full capture of this bench's render kernel (profiles/r1i_ncu_full_bench_kernel.csv, C2, mode B):
+# From the ncu --set full capture of this bench's render kernel (profiles/r1k_ncu_full_bench_kernel.csv, C2, mode B):
 # warp-level instructions executed per ray and DRAM bytes per launch.  Used only for the derived
 # "issue_slots_frac_est" / "traffic" fields; the primary roofline numbers are measured live.
-NCU_WARP_INST_PER_RAY = {"C2": 243475176833 / 4561710601}
-NCU_DRAM_BYTES_PER_LAUNCH = {"C2": 11839744 + 60595456}
+NCU_WARP_INST_PER_RAY = {"C2": 247536525255 / 4561710601}
+NCU_DRAM_BYTES_PER_LAUNCH = {"C2": 21506226000 + 33954349000}
 
 
 def measured_peaks():
@@ -285,9 +285,10 @@ def main():
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload) if not reduced else None,
             "issue_slots_frac_est": (k_rays * NCU_WARP_INST_PER_RAY[args.workload] / (k_ms * 1e-3) / (sm_count * 4 * max_mhz * 1e6))
             if args.workload in NCU_WARP_INST_PER_RAY else None,
-            "note": "bound = SM instruction issue on divergent code (ncu r1i: issue slots 68 % busy at 6 warps per scheduler, 22.6 of 32 "
-                    "lanes active per instruction, FP32 pipe 23 %, HBM idle: 72 MB per launch, the path pool lives in L2); 'achieved' "
-                    "counts the reference algorithm's flops per ray (SURVEY 8d)",
+            "note": "bound = SM instruction issue on divergent code (ncu r1k: issue slots 68 % busy at 6 warps per scheduler, 22.8 of 32 "
+                    "lanes active per instruction, FP32 pipe 23 %; HBM 55 GB per launch = 175 GB/s, almost all of it the 16 B per path of "
+                    "the sample staging array, the path pool lives in L2); 'achieved' counts the reference algorithm's flops per ray "
+                    "(SURVEY 8d)",
             "frac_at_clock_under_load": (achieved / (fp32_peak * clocks["sm_mhz"] / max_mhz)) if clocks and clocks.get("sm_mhz") else None,
         }
         line = {
