@@ -495,7 +495,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     }
     // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
     const uint32_t ns = p->sample_end - p->sample_begin;
-    const bool binned = s->binned > 0 && ns <= kMaxStageItems;   // mode B takes any sample count that fits its staging array
+    // mode B takes any sample count that fits its staging array; a parked path keeps its depth (and its count of
+    // nested dielectrics, which is bounded by the depth) in 8 bits
+    const bool binned = s->binned > 0 && ns <= kMaxStageItems && p->max_bounces <= 255u;
     const bool mode_w = binned || ns >= 32;
     // measured (profiles/r1_notes.md): tree scenes want 96 registers; list scenes 64 registers / 8 blocks in modes
     // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)

@@ -244,3 +244,15 @@ def test_binned_result_does_not_depend_on_the_schedule(monkeypatch):
         assert st["mode"] == 3
         if ref is None: ref = acc
         else: np.testing.assert_array_equal(acc, ref)
+
+
+def test_deep_paths_fall_back_to_mode_w():
+    """A bounce limit above 255 does not fit the parked path's 8-bit depth field: such launches use mode W."""
+    acc, st = _gpu_render(5, 96, 54, 36, depth=300)
+    assert st["mode"] == 1
+    ref, st2 = _gpu_render(5, 96, 54, 36, depth=255)
+    assert st2["mode"] == 3
+    # in the Cornell box paths practically never reach 255 bounces, so the two images agree sample for sample
+    np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-4)
+    assert res["frac_ok"] >= MIN_FRAC, res
