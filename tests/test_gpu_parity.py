@@ -256,3 +256,21 @@ def test_deep_paths_fall_back_to_mode_w():
     np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
     res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-4)
     assert res["frac_ok"] >= MIN_FRAC, res
+
+
+@needs_ref
+@pytest.mark.parametrize("binned", [None, "0"])
+def test_ragged_frames_and_slices_vs_oracle(binned, monkeypatch):
+    """Edge shapes against the oracle in mode B (default) and modes W / P: fewer pixels than lanes, sample counts that
+    are not multiples of 32, a sample slice that starts and ends inside the grid, a scene with a BVH."""
+    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)
+    else: monkeypatch.setenv("MRT_BINNED", binned)
+    for scene, w, h, spp, s0, s1 in [(5, 7, 3, 1, 0, 1), (5, 33, 5, 4, 0, 4), (6, 5, 1, 49, 0, 49), (0, 31, 9, 36, 0, 36),
+                                      (5, 40, 22, 16, 5, 12), (8, 24, 13, 100, 37, 90)]:
+        ref, meta = oracle_util.ref_render(scene, w, h, spp, s0=s0, s1=s1)
+        acc, st = _gpu_render(scene, w, h, spp, sample_begin=s0, sample_end=s1)
+        assert st["paths"] == w * h * (s1 - s0)
+        assert st["rays"] == meta["rays"], (scene, w, h, spp, st["rays"], meta["rays"])
+        np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+        res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=REL_TOL)
+        assert res["n_bad"] == 0, (scene, w, h, spp, res)
