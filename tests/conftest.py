@@ -24,3 +24,10 @@ def emul_bin():
     """TEST-ONLY g++ build of the device tracer core (tests/host_emul)."""
     import oracle_util
     return oracle_util.build_emul()
+
+
+@pytest.fixture(scope="session")
+def emul_kernel_bin():
+    """TEST-ONLY g++ build of the render kernels themselves behind a SIMT shim (tests/host_emul/emul_warp.h)."""
+    import oracle_util
+    return oracle_util.build_emul_binned()

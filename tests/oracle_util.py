@@ -81,3 +81,36 @@ def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=
         return acc, meta
     finally:
         os.unlink(path)
+
+
+def build_emul_binned():
+    """g++ build of tests/host_emul/emul_binned.cpp: the render kernels of render_kernels.cuh compiled for the CPU through
+    the SIMT shim emul_warp.h (lanes = fibers).  TEST-ONLY; needs the CUDA headers for the vector types."""
+    out_dir = os.path.join(ROOT, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "emul_binned")
+    srcs = [os.path.join(ROOT, "tests", "host_emul", "emul_binned.cpp")] + \
+           [os.path.join(CSRC, f) for f in ("scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "flatten.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("trace_core.h", "render_kernels.cuh", "gpu_internal.h", "scene_graph.h")] + \
+           [os.path.join(ROOT, "tests", "host_emul", "emul_warp.h"), os.path.join(ROOT, "include", "mrt_types.h")]
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-w", "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-I", cuda_inc] +
+                       srcs + ["-o", exe], check=True)
+    return exe
+
+
+def emul_binned(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, mode="B", chunk=0, bins=2):
+    from miniraytracer_b200.accfile import read_acc
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        path = f.name
+    try:
+        r = subprocess.run([exe, "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(spp),
+                            "-depth", str(depth), "-seed", str(seed), "-s0", str(s0), "-s1", str(s1), "-mode", mode,
+                            "-chunk", str(chunk), "-bins", str(bins), "-assets", ASSETS, "-out", path],
+                           check=True, capture_output=True, text=True)
+        acc, meta = read_acc(path)
+        meta["info"] = json.loads(r.stdout.strip().splitlines()[-1])
+        return acc, meta
+    finally:
+        os.unlink(path)

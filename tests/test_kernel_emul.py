@@ -1,0 +1,66 @@
+"""The render kernels themselves on the CPU.  tests/host_emul/emul_warp.h is a SIMT shim (every lane a fiber, the lanes
+of a warp switch at each warp collective) behind which g++ compiles render_kernels.cuh unchanged; emul_binned.cpp
+launches one block of four warps.  This checks the WARP-LEVEL logic that test_host_emul.py cannot see -- ticket queue,
+bins, path pool, sample staging, lane regeneration, chunk epilogues -- against the oracle, without a GPU.
+Test harness only: the shipped library has no CPU execution path."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util
+from miniraytracer_b200 import accfile
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+
+
+def _same(acc, ref, rays, ref_rays):
+    assert rays == ref_rays
+    np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
+    assert res["n_bad"] == 0, res
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp,bins", [(5, 24, 13, 36, 1), (5, 24, 13, 36, 2), (5, 24, 13, 36, 3), (6, 20, 11, 36, 2),
+                                                 (7, 20, 11, 16, 2), (8, 16, 9, 16, 2), (0, 16, 16, 9, 2), (5, 7, 3, 1, 2)])
+def test_mode_b_kernel_matches_oracle(emul_kernel_bin, scene, w, h, spp, bins):
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp)
+    acc, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, bins=bins)
+    assert meta["info"]["tasks"] > 4 or w * h < 32          # several tickets per warp
+    _same(acc, ref, meta["rays"], rmeta["rays"])
+
+
+@needs_ref
+def test_mode_b_result_is_schedule_independent(emul_kernel_bin):
+    """Finished samples are summed per pixel in item order from the staging array: chunk size and bins do not change a bit."""
+    base, _ = oracle_util.emul_binned(emul_kernel_bin, 6, 20, 11, 64, bins=1, chunk=1)
+    for bins, chunk in ((2, 1), (3, 2), (2, 5), (2, 128)):
+        acc, meta = oracle_util.emul_binned(emul_kernel_bin, 6, 20, 11, 64, bins=bins, chunk=chunk)
+        np.testing.assert_array_equal(acc, base)
+
+
+@needs_ref
+def test_mode_b_sample_slice(emul_kernel_bin):
+    ref, rmeta = oracle_util.ref_render(5, 20, 11, 49, s0=10, s1=37)
+    acc, meta = oracle_util.emul_binned(emul_kernel_bin, 5, 20, 11, 49, s0=10, s1=37)
+    _same(acc, ref, meta["rays"], rmeta["rays"])
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,scene,w,h,spp", [("W", 5, 20, 11, 36), ("W", 7, 16, 9, 36), ("P", 5, 40, 11, 9), ("P", 0, 33, 7, 4)])
+def test_modes_w_and_p_kernels_match_oracle(emul_kernel_bin, mode, scene, w, h, spp):
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp)
+    acc, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, mode=mode)
+    _same(acc, ref, meta["rays"], rmeta["rays"])
+
+
+def test_mode_b_kernel_matches_golden_without_the_reference(emul_kernel_bin):
+    """Same check against a committed golden fixture, so it also runs where oracle/_ref is absent."""
+    g = np.load(os.path.join(GOLDEN, "golden_scene5.npz"))
+    w, h, spp, depth = int(g["width"]), int(g["height"]), int(g["spp"]), int(g["depth"])
+    if w * h * spp > 400000:
+        pytest.skip("golden frame too large for the fiber emulation")
+    acc, meta = oracle_util.emul_binned(emul_kernel_bin, 5, w, h, spp, depth=depth)
+    _same(acc, g["acc"], meta["rays"], int(g["rays"]))
