@@ -5,9 +5,10 @@
 // Work decomposition (replaces work_queue.cpp + the draw() loop nest, main.cpp:138-188):
 //   * persistent warps: the grid is sized to the SM count x resident blocks and every warp pulls work from
 //     one global atomic ticket counter (one atomic per warp task, issued by lane 0, broadcast by shuffle);
-//   * a warp task is a POOL of (pixel, sample) items that the 32 lanes drain cooperatively: whenever a
-//     lane's path terminates it is regenerated from the pool at the next warp-converged point (ballot +
-//     popc prefix), so lanes do not idle while the longest path of a batch finishes;
+//   * a warp task is a chunk of (pixel, sample) items that the 32 lanes drain cooperatively.  Mode B (default)
+//     regroups the live paths between segments through a per-warp pool and bins; in modes W / P a lane keeps
+//     its path and is regenerated from the item stream at the next warp-converged point (ballot + popc
+//     prefix), so lanes do not idle while the longest path of a batch finishes;
 //   * per-thread traversal stacks live in shared memory, interleaved by lane (word k of lane l at
 //     [k*32 + l]) so pushes/pops are bank-conflict free.
 // Every accumulator element has exactly one writer: no float atomics, results are reproducible run to run.
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
 //   * pops 32 paths from the fullest bin if it holds 32            -> 32 lanes that will do similar things,
 //   * else starts 32 new paths (consecutive samples of a pixel)    -> primary rays, fully coherent,
 //   * else (chunk drained) pops what is left,
-// runs ONE segment for them (path_step, single call site), adds finished paths to the per-lane partial sums
-// part[k][lane] and parks the survivors again.  The schedule depends only on the paths themselves, so the
-// result is reproducible run to run; per-path arithmetic is untouched (same RNG stream, same operations).
+// runs ONE segment for them (path_step, single call site), writes finished samples to the chunk's staging array
+// (global memory, one float4 per item) and parks the survivors again.  At the end of the chunk every pixel's
+// samples are summed from the staging array in item order, so the result does not depend on the schedule at all;
+// per-path arithmetic is untouched (same RNG stream, same operations).
 // A live path carries no radiance (only lights and the sky emit, and both end the path), so L is not parked.
 __device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const Path &p, const Rng &rng, uint32_t item) {
     uint32_t *q = pool + slot;
