@@ -95,6 +95,24 @@ typedef struct MrtScene MrtScene;
 /* Copies the flattened scene to the current device.  The description and everything it
  * points to may be freed afterwards. */
 int mrt_gpu_scene_upload(const MrtSceneDesc *desc, MrtScene **out);
+/* Scheduling knobs of the renderer (A/B measurements, tests).  Zero-initialised = the measured defaults; none of
+ * them changes a result beyond float summation order (modes) -- see DESIGN.md section 4.  The library reads no
+ * environment variables. */
+typedef struct MrtTuning {
+    uint32_t mode;         /* MRT_MODE_AUTO, or force MRT_MODE_PER_LANE / MRT_MODE_PER_WARP / MRT_MODE_BINNED */
+    uint32_t bins;         /* mode B: 0 = classifier bins (default), 1 = one bin, 2 = classifier bins, 3 = + pending-weight bit */
+    uint32_t min_blocks;   /* launch-bounds variant: resident blocks per SM, 5..8 (0 = by scene type) */
+    uint32_t chunk_pixels; /* pixels per warp task (0 = automatic) */
+    uint32_t variant_all;  /* 1 = the unspecialised kernel (all scene features compiled in) */
+    uint32_t z_order;      /* 1 = hand out pixels along a Z-curve instead of row-major */
+    uint32_t coop_trees;   /* BVH trees: 0 = default, 1 = per-lane traversal, 2 = warp-cooperative traversal */
+    uint32_t reserved[9];
+} MrtTuning;
+#define MRT_MODE_AUTO 0u
+#define MRT_MODE_PER_LANE 1u /* a lane owns a pixel and adds its samples in the reference's order (main.cpp:154-166) */
+#define MRT_MODE_PER_WARP 2u /* a warp owns a chunk of pixels; lanes keep their paths */
+#define MRT_MODE_BINNED 3u   /* a warp owns a chunk; paths are parked and regrouped between segments (default) */
+int mrt_gpu_set_tuning(MrtScene *s, const MrtTuning *t /* NULL = defaults */);
 /* Launch on this CUDA stream (a cudaStream_t passed as void*; NULL = default stream). */
 int mrt_gpu_set_stream(MrtScene *s, void *cuda_stream);
 /* Render into caller-owned device memory (width*height float4) instead of the library's own
@@ -116,7 +134,8 @@ typedef struct MrtRenderStats {
     uint64_t nonfinite;  /* samples dropped by the finite check (main.cpp:163-165) */
     uint64_t warp_iterations; /* segment steps executed per warp, summed: rays / (32 * this) = share of lanes with a live path */
     float kernel_ms;     /* CUDA-event time of the render kernel on its stream */
-    uint32_t grid, block, smem_bytes, mode;
+    uint32_t grid, block, smem_bytes;
+    uint32_t mode;       /* MRT_MODE_* of the kernel that ran */
 } MrtRenderStats;
 /* Statistics of the last finished render (blocks like mrt_gpu_wait). */
 int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out);

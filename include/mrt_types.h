@@ -157,6 +157,12 @@ typedef struct MrtRenderParams {
     uint64_t seed;            /* PCG32 initstate; the stream (initseq) is (y*W+x)*N+s */
     float max_luminance;      /* applied by finalize only (main.cpp:170-173) */
     uint32_t flags;           /* MRT_RENDER_* */
+    /* Crop window: only pixels [crop_x0, crop_x1) x [crop_y0, crop_y1) of the width x height frame are rendered and
+       the accumulator holds (crop_x1-crop_x0) x (crop_y1-crop_y0) pixels, row-major.  Sub-pixel positions (u, v) and
+       PCG32 stream ids stay those of the FULL frame (main.cpp:156-157), so a window is bit-identical to the same
+       pixels of a full render -- used for tile sharding and for parity checks at full-size configurations.
+       All four zero = the whole frame. */
+    uint32_t crop_x0, crop_y0, crop_x1, crop_y1;
 } MrtRenderParams;
 
 #define MRT_RENDER_ACCUMULATE 1u /* add to the accumulator instead of overwriting it */

@@ -48,7 +48,17 @@ class SceneDesc(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples", C.c_uint32),
                 ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32), ("max_bounces", C.c_uint32),
-                ("seed", C.c_uint64), ("max_luminance", C.c_float), ("flags", C.c_uint32)]
+                ("seed", C.c_uint64), ("max_luminance", C.c_float), ("flags", C.c_uint32),
+                ("crop_x0", C.c_uint32), ("crop_y0", C.c_uint32), ("crop_x1", C.c_uint32), ("crop_y1", C.c_uint32)]
+
+
+class Tuning(C.Structure):
+    """MrtTuning: scheduling knobs (all zero = the measured defaults)."""
+    _fields_ = [("mode", C.c_uint32), ("bins", C.c_uint32), ("min_blocks", C.c_uint32), ("chunk_pixels", C.c_uint32),
+                ("variant_all", C.c_uint32), ("z_order", C.c_uint32), ("coop_trees", C.c_uint32), ("reserved", C.c_uint32 * 9)]
+
+
+MODE_AUTO, MODE_PER_LANE, MODE_PER_WARP, MODE_BINNED = 0, 1, 2, 3
 
 
 class Params(C.Structure):
@@ -76,7 +86,7 @@ DEFAULT_SEED = 11350390909718046443  # main.cpp:302
 # every symbol include/mrt_gpu.h declares
 EXPORTS = [
     "mrt_last_error", "mrt_params_default", "mrt_params_parse", "mrt_scene_create", "mrt_scene_desc",
-    "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_stream",
+    "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_tuning", "mrt_gpu_set_stream",
     "mrt_gpu_bind_accumulator", "mrt_gpu_render_async", "mrt_gpu_poll", "mrt_gpu_wait", "mrt_gpu_stats",
     "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_cancel", "mrt_gpu_destroy",
 ]
@@ -119,6 +129,7 @@ def load(build_if_missing=True):
     lib.mrt_scene_free.restype = None
     lib.mrt_gpu_init.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
     lib.mrt_gpu_scene_upload.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
+    lib.mrt_gpu_set_tuning.argtypes = [vp, C.POINTER(Tuning)]
     lib.mrt_gpu_set_stream.argtypes = [vp, vp]
     lib.mrt_gpu_bind_accumulator.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
     lib.mrt_gpu_render_async.argtypes = [vp, C.POINTER(RenderParams)]
@@ -204,7 +215,7 @@ class HostScene:
 class Renderer:
     """A scene resident on one GPU (mrt_gpu_scene_upload) + render / readback calls."""
 
-    def __init__(self, host_scene, device=0):
+    def __init__(self, host_scene, device=0, tuning=None):
         lib = load()
         self._lib = lib
         self.info = DeviceInfo()
@@ -213,6 +224,18 @@ class Renderer:
         self._h = C.c_void_p()
         _check(lib.mrt_gpu_scene_upload(host_scene.desc, C.byref(self._h)))
         self._size = None
+        if tuning:
+            self.set_tuning(**tuning)
+
+    def set_tuning(self, **kw):
+        """mrt_gpu_set_tuning: keyword = MrtTuning field (mode, bins, min_blocks, chunk_pixels, variant_all, z_order,
+        coop_trees); no keywords = back to the defaults."""
+        t = Tuning()
+        for k, v in kw.items():
+            if k not in dict(Tuning._fields_) or k == "reserved":
+                raise MrtError(f"unknown tuning field {k!r}")
+            setattr(t, k, int(v))
+        _check(self._lib.mrt_gpu_set_tuning(self._h, C.byref(t)))
 
     def set_stream(self, cuda_stream_ptr):
         _check(self._lib.mrt_gpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
@@ -221,12 +244,15 @@ class Renderer:
         _check(self._lib.mrt_gpu_bind_accumulator(self._h, C.c_void_p(device_ptr), width, height))
 
     def render_async(self, width, height, spp, depth=32, seed=DEFAULT_SEED, sample_begin=0, sample_end=None,
-                     max_luminance=1000.0, accumulate=False):
+                     max_luminance=1000.0, accumulate=False, crop=None):
+        """crop = (x0, y0, x1, y1): render only that window of the width x height frame; the accumulator (and every
+        readback) then has the window's size."""
         n = grid_samples(spp)
+        x0, y0, x1, y1 = crop if crop else (0, 0, 0, 0)
         p = RenderParams(width, height, n, sample_begin, n if sample_end is None else sample_end, depth, seed,
-                         max_luminance, MRT_RENDER_ACCUMULATE if accumulate else 0)
+                         max_luminance, MRT_RENDER_ACCUMULATE if accumulate else 0, x0, y0, x1, y1)
         _check(self._lib.mrt_gpu_render_async(self._h, C.byref(p)))
-        self._size = (width, height)
+        self._size = (x1 - x0, y1 - y0) if crop else (width, height)
         return p
 
     def poll(self):
@@ -279,12 +305,12 @@ class Renderer:
             pass
 
 
-def render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, device=0, asset_dir=None, finalize=False):
+def render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, device=0, asset_dir=None, finalize=False, tuning=None, **kw):
     """One-call convenience: build + upload the scene, render all samples, return (image, stats)."""
     hs = HostScene(scene, width, height, asset_dir)
-    r = Renderer(hs, device)
+    r = Renderer(hs, device, tuning)
     try:
-        r.render_async(width, height, spp, depth, seed)
+        r.render_async(width, height, spp, depth, seed, **kw)
         st = r.stats()
         return r.readback(finalize=finalize), st
     finally:

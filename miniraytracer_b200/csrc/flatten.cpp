@@ -22,9 +22,10 @@ struct Flattener {
     std::map<int, uint32_t> mat_memo;    // graph material -> flat material index
     std::map<int, uint32_t> tex_memo;
     std::vector<uint64_t> image_offset;
+    FlattenOptions opt;
     bool ok = true;
 
-    Flattener(const SceneGraph &g_, FlatScene &o_) : g(g_), o(o_) {}
+    Flattener(const SceneGraph &g_, FlatScene &o_, const FlattenOptions &opt_) : g(g_), o(o_), opt(opt_) {}
 
     void fail(const std::string &msg) { if (ok) o.error = msg; ok = false; }
 
@@ -237,8 +238,7 @@ struct Flattener {
             // cull box: the object's bounds in the parent frame (scene_object.cpp:20-27), inflated after the
             // whole scene is known (flatten_scene); w of the first record = 1 if there is one
             Aabb bb;
-            static const bool no_cull = getenv("MRT_NO_CULL") != nullptr;   // A/B switch for the parity test of the cull
-            const bool has = !no_cull && g.bounding_box(id, g.camera.time0, g.camera.time1, &bb);
+            const bool has = opt.cull_boxes && g.bounding_box(id, g.camera.time0, g.camera.time1, &bb);
             o.xlate.push_back(has ? f4(bb.min.x, bb.min.y, bb.min.z, ubits(1u)) : f4(0, 0, 0, ubits(0u)));
             o.xlate.push_back(has ? f4(bb.max.x, bb.max.y, bb.max.z, 0) : f4(0, 0, 0, 0));
             ref = MRT_REF(MRT_T_TRANSLATE, i / 3);
@@ -314,10 +314,10 @@ struct Flattener {
 };
 }  // namespace
 
-bool flatten_scene(const SceneGraph &g, FlatScene *out) {
+bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &opt) {
     FlatScene &o = *out;
     o = FlatScene();
-    Flattener fl(g, o);
+    Flattener fl(g, o, opt);
     uint64_t off = 0;
     for (const Image &im : g.images) {
         fl.image_offset.push_back(off);

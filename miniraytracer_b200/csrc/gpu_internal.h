@@ -1,4 +1,4 @@
-// Internal state shared by the device-side translation units (render_kernel.cu, render_wavefront.cu).
+// Internal state of the device half of the C ABI (render_kernel.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -28,11 +28,9 @@ struct MrtScene {
     std::vector<void *> allocs;
     mrt::SceneView view;
     uint32_t stack_words = 0;
-    int min_blocks = 0;           // launch-bounds variant (MRT_MINB); 0 = by scene: 5 (96 regs) with BVH trees, else 6 (80 regs)
+    MrtTuning tuning = {};        // mrt_gpu_set_tuning; all zero = measured defaults
     uint32_t has_trees = 0;
-    uint32_t chunk_pixels = 0;    // pixels per warp task (MRT_CHUNK, 0 = automatic)
     uint32_t features = 0;        // MRT_FEAT_* mask of the scene -> kernel variant (render_variants.h)
-    int force_all = 0;            // MRT_VARIANT_ALL=1: always use the unspecialised kernels (tuning / A-B)
     cudaStream_t stream = nullptr;
     cudaStream_t poll_stream = nullptr;
     // accumulator
@@ -55,30 +53,17 @@ struct MrtScene {
     bool rendered = false;
     MrtRenderParams last;
     uint32_t last_tasks = 0, last_grid = 0, last_block = mrt::kBlock, last_smem = 0, last_mode = 0;
+    uint32_t last_w = 0, last_h = 0;   // size of the rendered window = of the accumulator
     float4 *last_acc = nullptr;
-    uint64_t last_rays = 0, last_iters = 0, last_nonfinite = 0;   // filled by the wavefront driver (it is synchronous)
-    bool last_wavefront = false;
     // pixel work order (Z-curve), rebuilt when the frame size changes
     uint32_t *order_dev = nullptr;
     uint32_t order_w = 0, order_h = 0;
-    int use_order = 0;            // MRT_ORDER=1: hand out pixels along a Z-curve (measured: no gain, default off)
     // binned mode (render_pixel_binned): path pool + classifier boxes of the root list's composite children
-    int binned = 0;               // MRT_BINNED: 0 = off, 1 = pool only (one bin), 2 = + classifier bins
     uint32_t *pool_dev = nullptr;
     size_t pool_words = 0;
     uint32_t *stage_dev = nullptr;   // finished samples of the chunks in flight (float4 per path)
     size_t stage_words = 0;
     uint32_t n_cls_boxes = 0;
     float cls_box[3][6];
-    // wavefront renderer state (render_wavefront.cu)
-    uint32_t has_volumes = 0;
-    int wavefront = 0;            // MRT_WAVEFRONT: 1 = use the wavefront renderer
-    void *wf_state = nullptr;
-    size_t wf_state_bytes = 0;
-    unsigned int *wf_ctrl = nullptr;
 };
-
-// render_wavefront.cu
-int mrt_wavefront_render(MrtScene *s, const MrtRenderParams *p, float4 *acc, uint32_t sqrt_n);
-void mrt_wavefront_free(MrtScene *s);
 

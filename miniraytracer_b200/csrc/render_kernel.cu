@@ -1,23 +1,6 @@
-// sm_100a render kernels + the device half of the C ABI (include/mrt_gpu.h).
-//
-// Work decomposition (replaces work_queue.cpp + the draw() loop nest,
-// main.cpp:138-188):
-//   * persistent warps: the grid is sized to the SM count x resident blocks and
-//     every warp pulls work from one global atomic ticket counter (one atomic
-//     per warp task, issued by lane 0 and broadcast with a shuffle);
-//   * a warp task is a small POOL of (pixel, sample) items that the 32 lanes
-//     drain cooperatively: whenever a lane's path terminates it is regenerated
-//     from the pool at the next warp-converged point (ballot + popc prefix), so
-//     lanes do not idle while the longest path of a batch finishes;
-//       mode W (>= 32 samples per pixel in this launch): pool = all samples of
-//              one pixel -> coherent primary rays; lane partial sums are
-//              combined with a fixed-order shuffle tree -> deterministic;
-//       mode P (< 32 samples): pool = a run of pixels; a lane owns a pixel and
-//              walks its samples in the reference's order (bit-identical sum);
-//   * per-thread traversal stacks live in shared memory, interleaved by lane
-//     (word k of lane l at [k*32 + l]) so pushes/pops are bank-conflict free.
-// Every accumulator element has exactly one writer: no float atomics, results
-// are reproducible run to run.
+// Device half of the C ABI (include/mrt_gpu.h): scene upload, launch configuration of the render kernels
+// (render_kernels.cuh -- the work decomposition is described there), finalize / tone-map kernels, readback.
+// The library reads no environment variables: scheduling knobs come in through mrt_gpu_set_tuning (MrtTuning).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -194,7 +177,6 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->rendered) cudaStreamSynchronize(s->stream);
-    mrt_wavefront_free(s);
     for (void *p : s->allocs) cudaFree(p);
     if (s->own_acc) cudaFree(s->own_acc);
     if (s->order_dev) cudaFree(s->order_dev);
@@ -356,16 +338,8 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     v.sky = d->sky;
     v.cam = d->camera;
     s->stack_words = d->stack_words ? d->stack_words : 64;
-    if (const char *e = getenv("MRT_MINB")) s->min_blocks = atoi(e);
-    if (const char *e = getenv("MRT_CHUNK")) s->chunk_pixels = (uint32_t) atoi(e);
-    if (const char *e = getenv("MRT_WAVEFRONT")) s->wavefront = atoi(e);
-    if (const char *e = getenv("MRT_ORDER")) s->use_order = atoi(e);
-    s->has_volumes = d->n_vol ? 1u : 0u;
     s->has_trees = d->n_node2 ? 1u : 0u;
     s->features = d->features;
-    if (const char *e = getenv("MRT_VARIANT_ALL")) s->force_all = atoi(e);
-    s->binned = 2;   // mode B with classifier bins is the default for >= 32 samples per launch (measured, profiles/r1_notes.md)
-    if (const char *e = getenv("MRT_BINNED")) s->binned = atoi(e);
     find_classifier_boxes(d, s);
 
     auto cu = [&](cudaError_t e, const char *what) {
@@ -385,6 +359,19 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (!cu(cudaEventCreate(&s->ev0), "cudaEventCreate")) return fail(MRT_E_CUDA);
     if (!cu(cudaEventCreate(&s->ev1), "cudaEventCreate")) return fail(MRT_E_CUDA);
     *out = s;
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_set_tuning(MrtScene *s, const MrtTuning *t) {
+    if (!s) { set_error("null scene"); return MRT_E_INVALID; }
+    MrtTuning z;
+    memset(&z, 0, sizeof(z));
+    if (t) z = *t;
+    if (z.mode > MRT_MODE_BINNED || z.bins > 3u || (z.min_blocks && (z.min_blocks < 5u || z.min_blocks > 8u)) || z.coop_trees > 2u) {
+        set_error("mrt_gpu_set_tuning: value out of range");
+        return MRT_E_INVALID;
+    }
+    s->tuning = z;
     return MRT_OK;
 }
 
@@ -444,14 +431,19 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     while ((uint64_t) (sq + 1) * (sq + 1) <= p->samples) sq++;
     while ((uint64_t) sq * sq > p->samples) sq--;
     if (sq * sq != p->samples) { set_error("mrt_gpu_render_async: samples must be a perfect square (main.cpp:319-320)"); return MRT_E_INVALID; }
-    const uint64_t n_pixels64 = (uint64_t) p->width * p->height;
+    // crop window (all zero = the whole frame): the accumulator has the window's size
+    uint32_t cx0 = p->crop_x0, cy0 = p->crop_y0, cx1 = p->crop_x1, cy1 = p->crop_y1;
+    if (!(cx0 | cy0 | cx1 | cy1)) { cx1 = p->width; cy1 = p->height; }
+    if (cx0 >= cx1 || cy0 >= cy1 || cx1 > p->width || cy1 > p->height) { set_error("mrt_gpu_render_async: bad crop window"); return MRT_E_INVALID; }
+    const uint32_t cw = cx1 - cx0, ch = cy1 - cy0;
+    const uint64_t n_pixels64 = (uint64_t) cw * ch;
     if (n_pixels64 > 0x7FFFFFFFull) { set_error("image too large"); return MRT_E_INVALID; }
     const uint32_t n_pixels = (uint32_t) n_pixels64;
     CUDA_TRY(cudaSetDevice(s->device));
 
     float4 *acc = nullptr;
     if (s->ext_acc) {
-        if (s->ext_w != p->width || s->ext_h != p->height) { set_error("bound accumulator has a different size"); return MRT_E_INVALID; }
+        if (s->ext_w != cw || s->ext_h != ch) { set_error("bound accumulator has a different size"); return MRT_E_INVALID; }
         acc = s->ext_acc;
     } else {
         if (s->own_acc_pixels != n_pixels) {
@@ -463,22 +455,10 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         acc = s->own_acc;
     }
 
-    if (s->wavefront) {   // wavefront renderer (render_wavefront.cu); synchronous host loop
-        CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
-        CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-        int rc = mrt_wavefront_render(s, p, acc, sq);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-        s->rendered = true;
-        s->last = *p;
-        s->last_tasks = 1; s->last_grid = 0; s->last_block = 128; s->last_smem = 0; s->last_mode = 2u;
-        s->last_acc = acc;
-        return MRT_OK;
-    }
-
     RenderArgs a;
     a.sc = s->view;
     a.width = p->width; a.height = p->height; a.sqrt_n = sq;
+    a.crop_x0 = cx0; a.crop_y0 = cy0; a.crop_w = cw; a.n_pixels = n_pixels;
     a.s_begin = p->sample_begin; a.s_end = p->sample_end; a.max_bounces = p->max_bounces;
     a.seed = p->seed;
     a.accumulate = (p->flags & MRT_RENDER_ACCUMULATE) ? 1u : 0u;
@@ -488,22 +468,26 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.counters = s->counters;
     a.cancel = s->cancel_dev;
     a.order = nullptr;
-    if (s->use_order) {
-        int rc = ensure_order(s, p->width, p->height);
+    const MrtTuning &tn = s->tuning;
+    if (tn.z_order) {
+        int rc = ensure_order(s, cw, ch);
         if (rc) return rc;
         a.order = s->order_dev;
     }
     // kernel variant: specialised for the scene's feature mask; launch bounds by scene type (measured)
     const uint32_t ns = p->sample_end - p->sample_begin;
-    // mode B takes any sample count that fits its staging array; a parked path keeps its depth (and its count of
-    // nested dielectrics, which is bounded by the depth) in 8 bits
-    const bool binned = s->binned > 0 && ns <= kMaxStageItems && p->max_bounces <= 255u;
-    const bool mode_w = binned || ns >= 32;
+    // Mode B (default) takes any sample count that fits its staging array; a parked path keeps its depth (and its
+    // count of nested dielectrics, which is bounded by the depth) in 8 bits.  Otherwise mode W for >= 32 samples per
+    // launch, else mode P.  MrtTuning.mode forces a mode where it is applicable.
+    const bool can_bin = ns <= kMaxStageItems && p->max_bounces <= 255u;
+    bool binned = can_bin, mode_w = can_bin || ns >= 32;
+    if (tn.mode == MRT_MODE_PER_LANE) { binned = false; mode_w = false; }
+    else if (tn.mode == MRT_MODE_PER_WARP) { binned = false; mode_w = true; }
+    else if (tn.mode == MRT_MODE_BINNED && !can_bin) { set_error("mrt_gpu_render_async: mode B needs <= 8192 samples per launch and <= 255 bounces"); return MRT_E_INVALID; }
     // measured (profiles/r1_notes.md): tree scenes want 96 registers; list scenes 64 registers / 8 blocks in modes
     // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)
-    int minb = s->min_blocks ? s->min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
-    if (minb < 5 || minb > 8) minb = 6;
-    const Variant *variant = s->force_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
+    int minb = tn.min_blocks ? (int) tn.min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
+    const Variant *variant = tn.variant_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
     const void *kernel = variant->get(binned ? 2 : (mode_w ? 1 : 0), minb);
     uint32_t n_bins = 1;
     a.pool = nullptr;
@@ -511,9 +495,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.stage_items = 0;
     a.n_cls_boxes = 0;
     a.cls_pending = 0;
-    if (binned && s->binned >= 2) {
+    if (binned && tn.bins != 1u) {
         a.n_cls_boxes = s->n_cls_boxes;
-        a.cls_pending = (s->binned >= 3) ? 1u : 0u;
+        a.cls_pending = (tn.bins == 3u) ? 1u : 0u;
         memcpy(a.cls_box, s->cls_box, sizeof(a.cls_box));
         n_bins = 1u << (a.n_cls_boxes + a.cls_pending);
     }
@@ -550,7 +534,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         if (target > 4096u) target = 4096u;
         if (target < 256u) target = 256u;
         K = (uint32_t) (target / ns);
-        if (s->chunk_pixels) K = s->chunk_pixels;
+        if (tn.chunk_pixels) K = tn.chunk_pixels;
         if (K < 1u) K = 1u;
         if ((uint64_t) K * ns > kMaxStageItems) K = kMaxStageItems / ns;
         if (K > n_pixels) K = n_pixels;
@@ -562,18 +546,18 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         uint32_t k_auto = (4096u + ns - 1u) / ns;
         if (k_auto > 8u) k_auto = 8u;
         if (k_auto < 1u) k_auto = 1u;
-        K = s->chunk_pixels ? s->chunk_pixels : k_auto;
+        K = tn.chunk_pixels ? tn.chunk_pixels : k_auto;
         for (;;) {
             int rc = occupancy(K);
             if (rc) return rc;
-            if (K == 1 || s->chunk_pixels) break;
+            if (K == 1 || tn.chunk_pixels) break;
             if (blocks_per_sm >= minb && n_pixels / K >= 32u * resident_warps) break;
             K >>= 1;
         }
     } else {
         int rc = occupancy(0);
         if (rc) return rc;
-        K = s->chunk_pixels ? s->chunk_pixels : n_pixels / (8u * resident_warps);
+        K = tn.chunk_pixels ? tn.chunk_pixels : n_pixels / (8u * resident_warps);
         K = (K + 31u) & ~31u;
         if (K < 32u) K = 32u;
         if (K > 1024u) K = 1024u;
@@ -610,11 +594,12 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     s->rendered = true;
     s->last = *p;
+    s->last_w = cw; s->last_h = ch;
     s->last_tasks = a.n_tasks;
     s->last_grid = grid;
     s->last_block = threads;
     s->last_smem = (uint32_t) smem;
-    s->last_mode = binned ? 3u : (mode_w ? 1u : 0u);
+    s->last_mode = binned ? MRT_MODE_BINNED : (mode_w ? MRT_MODE_PER_WARP : MRT_MODE_PER_LANE);
     s->last_acc = acc;
     return MRT_OK;
 }
@@ -663,7 +648,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     CUDA_TRY(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->rays = c[0];
-    out->paths = (uint64_t) s->last.width * s->last.height * (s->last.sample_end - s->last.sample_begin);
+    out->paths = (uint64_t) s->last_w * s->last_h * (s->last.sample_end - s->last.sample_begin);
     out->nonfinite = c[2];
     out->warp_iterations = c[1];
     CUDA_TRY(cudaEventElapsedTime(&out->kernel_ms, s->ev0, s->ev1));
@@ -699,12 +684,12 @@ extern "C" int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize) {
     if (!s || !rgba_host) { set_error("mrt_gpu_readback: null argument"); return MRT_E_INVALID; }
     if (!s->rendered) { set_error("mrt_gpu_readback: nothing rendered yet"); return MRT_E_STATE; }
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t n = (size_t) s->last.width * s->last.height;
+    const size_t n = (size_t) s->last_w * s->last_h;
     const float4 *src = s->last_acc;
     if (finalize) {
         int rc = ensure_final(s, n);
         if (rc) return rc;
-        rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last.width, s->last.height, s->last.max_luminance);
+        rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
         if (rc) return rc;
         src = s->final_buf;
     }
@@ -717,10 +702,10 @@ extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
     if (!s || !argb_host) { set_error("mrt_gpu_tonemap: null argument"); return MRT_E_INVALID; }
     if (!s->rendered) { set_error("mrt_gpu_tonemap: nothing rendered yet"); return MRT_E_STATE; }
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t n = (size_t) s->last.width * s->last.height;
+    const size_t n = (size_t) s->last_w * s->last_h;
     int rc = ensure_final(s, n);
     if (rc) return rc;
-    rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last.width, s->last.height, s->last.max_luminance);
+    rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(s->max_bits, 0, sizeof(unsigned int), s->stream));
     max_luminance_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(s->final_buf, (uint32_t) n, s->max_bits);

@@ -25,7 +25,8 @@ constexpr uint32_t kMaxStageItems = 8192;   // item index has 14 bits in the par
 
 struct RenderArgs {
     SceneView sc;
-    uint32_t width, height, sqrt_n, s_begin, s_end, max_bounces;
+    uint32_t width, height, sqrt_n, s_begin, s_end, max_bounces;   // width x height = the FULL frame (sub-pixel positions, stream ids)
+    uint32_t crop_x0, crop_y0, crop_w, n_pixels;                   // rendered window: accumulator pixel i = (crop_x0 + i % crop_w, crop_y0 + i / crop_w)
     uint64_t seed;
     uint32_t accumulate;
     uint32_t stack_words;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
     const uint32_t K = a.pixels_per_task;
     float4 *part = reinterpret_cast<float4 *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * K * 32u + lane;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t n_pixels = a.n_pixels;
     const uint32_t ns = a.s_end - a.s_begin;
     unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_warp(const Rend
                         cur_k = k;
                     }
                     const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
-                    const uint32_t y = pix / a.width, x = pix - y * a.width;
+                    const uint32_t cy = pix / a.crop_w, x = a.crop_x0 + (pix - cy * a.crop_w), y = a.crop_y0 + cy;
                     path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
                     alive = true;
                 }
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
     st.stride = 32u;
     st.sp = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t n_pixels = a.n_pixels;
     unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
     for (;;) {
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
                 const uint32_t cand = next_p + __popc(need & lt_mask);
                 if (cand < end_p) {
                     pix = a.order ? __ldg(a.order + cand) : cand;
-                    y = pix / a.width; x = pix - y * a.width;
+                    y = pix / a.crop_w; x = a.crop_x0 + (pix - y * a.crop_w); y += a.crop_y0;
                     s = a.s_begin;
                     sr = sg = sb = sc = 0;
                     has_pixel = true;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     // which path, the chunk size does not depend on the samples per pixel, and no shared memory is needed for sums
     float4 *stage = a.stage + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) a.stage_items;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.width * a.height;
+    const uint32_t n_pixels = a.n_pixels;
     const uint32_t ns = a.s_end - a.s_begin;
     unsigned long long rays = 0, nonfinite = 0, iters = 0;
 
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
                     const uint32_t kk = k / ns;
                     const uint32_t s = a.s_begin + (k - kk * ns);
                     const uint32_t pix = a.order ? __ldg(a.order + pix0 + kk) : pix0 + kk;
-                    const uint32_t y = pix / a.width, x = pix - y * a.width;
+                    const uint32_t cy = pix / a.crop_w, x = a.crop_x0 + (pix - cy * a.crop_w), y = a.crop_y0 + cy;
                     path_begin(a.sc, p, rng, x, y, s, a.sqrt_n, a.width, a.height, a.seed);
                 }
                 next_i += n;

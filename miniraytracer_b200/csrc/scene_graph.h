@@ -185,6 +185,9 @@ struct FlatScene {
     MrtSceneDesc desc;
     std::string error;
 };
-bool flatten_scene(const SceneGraph &g, FlatScene *out);
+struct FlattenOptions {
+    bool cull_boxes = true;   // conservative cull boxes on translate nodes (trace_core.h: cull_miss); off = A/B for the parity test
+};
+bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &opt = FlattenOptions());
 
 }  // namespace mrt

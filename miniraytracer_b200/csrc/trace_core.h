@@ -661,255 +661,6 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
 }
 #undef probe
 
-// ------------------------------------------------------------- incremental traversal
-// The same traversal as intersect(), cut into single actions so that a persistent traversal kernel can
-// refill lanes whose ray has finished while the other lanes keep going (wavefront renderer).  One call of
-// trav_step performs one action selected by the lane's state:
-//   cur is a NODE2 ref      -> up to MRT_TRAV_BURST inner nodes (box tests, IF_MISS push / pop)
-//   cur is another ref      -> visit it (list header, tree root, triangle leaf, transform, volume)
-//   cur == NONE (returning) -> pop one frame and act on it (list continuation incl. the inline primitive
-//                              loop, transform restore, volume phases)
-#ifndef MRT_TRAV_BURST
-#define MRT_TRAV_BURST 4
-#endif
-#define MRT_CUR_NONE 0xFFFFFFFFu
-struct Trav {
-    float tmin0, tmin, tmax, main_tmax, vol_t1;
-    uint32_t cur, sp0;
-    bool ret, probe;
-};
-MRT_HD void trav_begin(const SceneView &sc, Trav &t, float tmin0, float tmax0, const Stack &st) {
-    t.tmin0 = tmin0; t.tmin = tmin0; t.tmax = tmax0; t.main_tmax = tmax0; t.vol_t1 = 0.0f;
-    t.cur = sc.root; t.sp0 = st.sp; t.ret = false; t.probe = false;
-}
-MRT_HD bool trav_active(const Trav &t, const Stack &st) { return (t.cur != MRT_CUR_NONE) || (st.sp != t.sp0); }
-MRT_HD bool trav_hit(const Trav &t) { return t.ret; }   // valid once !trav_active
-MRT_HD void trav_step(const SceneView &sc, Trav &t, Ray &ray, Hit &rec, Rng &rng, Stack &st, Counters *cnt) {
-    const float tmin0 = t.tmin0;
-    if (t.cur != MRT_CUR_NONE && MRT_REF_TYPE(t.cur) == MRT_T_NODE2) {
-        // ---------------------------------------------------------- inner nodes
-        // Node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
-        // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
-        // (IF_MISS frame).  t.tmin/t.tmax are constant inside a tree, so the child box tests made here are
-        // the ones the children would make on entry.
-        int burst = MRT_TRAV_BURST;
-        do {
-            const uint32_t ni = MRT_REF_INDEX(t.cur);
-            MrtF4 n0 = ld4(sc.node2, 4 * ni), n1 = ld4(sc.node2, 4 * ni + 1);
-            MrtF4 n2 = ld4(sc.node2, 4 * ni + 2), n3 = ld4(sc.node2, 4 * ni + 3);
-            const uint32_t w0 = f2u(n0.w), w1 = f2u(n1.w), flags = f2u(n2.w);
-            const uint32_t order = (w0 >> 28) | ((w1 >> 28) << 4);
-            const uint32_t left = w0 & 0x0FFFFFFFu, right = w1 & 0x0FFFFFFFu;
-            const bool hl = !(flags & 1u) || aabb_hit(n0, n1, ray, t.tmin, t.tmax);
-            const bool hr = !(flags & 2u) || aabb_hit(n2, n3, ray, t.tmin, t.tmax);
-            const bool lfirst = (order & ray.mask) != 0;
-            const bool h_first = lfirst ? hl : hr, h_second = lfirst ? hr : hl;
-            const uint32_t first = lfirst ? left : right, second = lfirst ? right : left;
-            if (cnt) cnt->aabb += (flags & 1u) + ((flags >> 1) & 1u);
-            if (h_first) {
-                if (h_second) st.push(MRT_FRAME(MRT_F_IF_MISS, second));
-                t.cur = first;
-            } else if (h_second) {
-                t.cur = second;
-            } else {
-                // both children missed: this subtree reports no hit; resume with the nearest pending
-                // farther child, if the frame on top of the stack is one
-                t.ret = false;
-                t.cur = MRT_CUR_NONE;
-                if (st.sp != t.sp0) {
-                    const uint32_t e = st.base[(st.sp - 1) * st.stride];
-                    if ((e >> 29) == MRT_F_IF_MISS) { st.sp--; t.cur = e & 0x0FFFFFFFu; }
-                }
-            }
-        } while (--burst > 0 && t.cur != MRT_CUR_NONE && MRT_REF_TYPE(t.cur) == MRT_T_NODE2);
-        return;
-    }
-
-    if (t.cur != MRT_CUR_NONE) {
-        // ------------------------------------------------------------- visit
-        const uint32_t type = MRT_REF_TYPE(t.cur), idx = MRT_REF_INDEX(t.cur);
-        t.ret = false;
-        uint32_t next = MRT_CUR_NONE;
-        switch (type) {
-        case MRT_T_LIST: {   // object_list: own box test, then the child loop (LIST frame)
-            MrtF4 l0 = ld4(sc.list, 2 * idx), l1 = ld4(sc.list, 2 * idx + 1);
-            if (f2u(l1.w) >> 31) {
-                if (cnt) cnt->aabb++;
-                if (!aabb_hit(l0, l1, ray, t.tmin, t.tmax)) break;
-            }
-            st.push(MRT_FRAME(MRT_F_LIST, f2u(l0.w)));
-            break;
-        }
-        case MRT_T_BVH: {   // root of a bvh_node / pod_bvh tree: its own box test (scene_object.h:211, triangle.h:175)
-            MrtF4 b0 = ld4(sc.bvh, 2 * idx), b1 = ld4(sc.bvh, 2 * idx + 1);
-            if (cnt) cnt->aabb++;
-            if (!aabb_hit(b0, b1, ray, t.tmin, t.tmax)) break;
-            next = f2u(b0.w);
-            break;
-        }
-        case MRT_T_TRILEAF: {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
-            const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
-            for (uint32_t i = 0; i < count; i++) {
-                if (cnt) cnt->tri++;
-                if (hit_triangle(sc, first + i, ray, t.tmin, t.tmax, !t.probe, rec)) {
-                    t.ret = true;
-                    t.tmax = rec.t;
-                }
-            }
-            break;
-        }
-        case MRT_T_TRANSLATE:     // scene_object.cpp:9-18
-        case MRT_T_ROTATE_Y: {    // scene_object.cpp:70-98
-            MrtF4 r0, r2;
-            if (type == MRT_T_ROTATE_Y) {
-                r0 = ld4(sc.rot, 3 * idx);
-                MrtF4 r1 = ld4(sc.rot, 3 * idx + 1);
-                if (f2u(r1.w)) {   // bbox pre-test
-                    if (cnt) cnt->aabb++;
-                    if (!aabb_hit(r0, r1, ray, t.tmin, t.tmax)) break;
-                }
-                r2 = ld4(sc.rot, 3 * idx + 2);
-            } else {
-                r0 = ld4(sc.xlate, 3 * idx);
-                r2 = r0;
-            }
-            if (cnt) cnt->xform++;
-            st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
-            st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
-            st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
-            st.push((uint32_t) ray.inside);
-            st.push(MRT_FRAME(type == MRT_T_ROTATE_Y ? MRT_F_ROT_END : MRT_F_XLATE_END, idx));
-            V3 d = ray.d;
-            if (type == MRT_T_ROTATE_Y) {
-                const float sin_t = r2.x, cos_t = r2.y;
-                V3 o = ray.o;
-                o.x = cos_t * ray.o.x - sin_t * ray.o.z;
-                o.z = cos_t * ray.o.z + sin_t * ray.o.x;
-                d.x = cos_t * ray.d.x - sin_t * ray.d.z;
-                d.z = cos_t * ray.d.z + sin_t * ray.d.x;
-                ray.o = o;
-            } else {
-                ray.o = ray.o - v3(r0);
-            }
-            ray.inside = 0;
-            ray_set_dir(ray, d);   // the ray ctor re-normalises (ray.h:30); isInside resets to 0
-            next = f2u(r0.w);
-            break;
-        }
-        case MRT_T_VOLUME: {      // volumes.cpp:5-36, first t.probe
-            MrtF4 vl = ld4(sc.vol, idx);
-            if (cnt) cnt->vol++;
-            st.push(MRT_FRAME(MRT_F_VOL1, idx));
-            t.main_tmax = t.tmax;
-            t.probe = true;
-            t.tmin = -FLT_MAX;
-            t.tmax = FLT_MAX;
-            next = f2u(vl.x);
-            break;
-        }
-        default:
-            break;
-        }
-        t.cur = next;
-        return;
-    }
-
-    // ---------------------------------------------------------------- return
-    {
-        uint32_t e = st.pop();
-        uint32_t tag = e >> 29;
-        if (tag == MRT_F_IF_MISS) {
-            // the closer child has reported: a hit ends the whole tree (drop every pending farther child)
-            if (t.ret) {
-                while (st.sp != t.sp0 && (st.base[(st.sp - 1) * st.stride] >> 29) == MRT_F_IF_MISS) st.sp--;
-            } else {
-                t.cur = e & 0x0FFFFFFFu;
-            }
-        } else if (tag == MRT_F_LIST) {
-            // closest-hit loop over the children (scene_object.h:88-95); primitives inline
-            uint32_t ci = e & 0x0FFFFFFFu;
-            bool found = ((e >> 28) & 1u) | (t.ret ? 1u : 0u);
-            t.ret = found;
-            for (;;) {
-                uint32_t c = ldu(sc.child, ci);
-                uint32_t ctype = MRT_REF_TYPE(c);
-                if (ctype == MRT_T_END) break;
-                ci++;
-                if (ctype == MRT_T_SPHERE) {
-                    if (cnt) cnt->sphere++;
-                    if (hit_sphere(MRT_FEAT_ALL, sc, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
-                } else if (ctype <= MRT_T_RECT_YZ) {
-                    if (cnt) cnt->rect++;
-                    if (hit_rect(MRT_FEAT_ALL, sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, t.tmin, t.tmax, !t.probe, rec)) { found = true; t.tmax = rec.t; }
-                } else {
-                    st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
-                    t.cur = c;
-                    break;
-                }
-                t.ret = found;
-            }
-        } else if (tag == MRT_F_XLATE_END || tag == MRT_F_ROT_END) {
-            ray.inside = (int) st.pop();
-            ray.inv.z = st.popf(); ray.inv.y = st.popf(); ray.inv.x = st.popf();
-            ray.d.z = st.popf(); ray.d.y = st.popf(); ray.d.x = st.popf();
-            ray.o.z = st.popf(); ray.o.y = st.popf(); ray.o.x = st.popf();
-            ray.mask = dir_mask(ray.d);
-            if (t.ret && !t.probe) {
-                uint32_t idx = e & 0x0FFFFFFFu;
-                if (tag == MRT_F_XLATE_END) {
-                    rec.p = rec.p + v3(ld4(sc.xlate, 3 * idx));
-                } else {
-                    MrtF4 r2 = ld4(sc.rot, 3 * idx + 2);
-                    float sin_t = r2.x, cos_t = r2.y;
-                    V3 p = rec.p, n = rec.n;
-                    p.x = cos_t * rec.p.x + sin_t * rec.p.z;
-                    p.z = cos_t * rec.p.z - sin_t * rec.p.x;
-                    n.x = cos_t * rec.n.x + sin_t * rec.n.z;
-                    n.z = cos_t * rec.n.z - sin_t * rec.n.x;
-                    rec.p = p;
-                    rec.n = n;
-                }
-            }
-        } else if (tag == MRT_F_VOL1) {
-            uint32_t idx = e & 0x0FFFFFFFu;
-            if (!t.ret) {
-                t.probe = false; t.tmin = t.tmin0; t.tmax = t.main_tmax;
-            } else {
-                t.vol_t1 = t.tmax;   // rec1.t
-                st.push(MRT_FRAME(MRT_F_VOL2, idx));
-                t.tmin = t.vol_t1 + 0.0001f;
-                t.tmax = FLT_MAX;
-                t.cur = f2u(ld4(sc.vol, idx).x);
-            }
-        } else {   // MRT_F_VOL2
-            uint32_t idx = e & 0x0FFFFFFFu;
-            float t2 = t.tmax;
-            bool both = t.ret;
-            t.probe = false; t.tmin = t.tmin0; t.tmax = t.main_tmax;
-            t.ret = false;
-            if (both) {
-                float t1 = t.vol_t1;
-                if (t1 < t.tmin) t1 = t.tmin;
-                if (t2 > t.tmax) t2 = t.tmax;
-                if (!(t1 >= t2)) {
-                    if (t1 < 0) t1 = 0;
-                    MrtF4 vl = ld4(sc.vol, idx);
-                    float inside_dist = (t2 - t1);
-                    float hit_dist = -(frcp(vl.y)) * cr_logf(randf(rng));
-                    if (hit_dist < inside_dist) {
-                        rec.t = t1 + hit_dist;
-                        rec.p = ray_eval(ray, rec.t);
-                        rec.n = v3(1, 0, 0);
-                        rec.mat = f2u(vl.z);
-                        t.tmax = rec.t;
-                        t.ret = true;
-                    }
-                }
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------- textures
 // texture.cpp:68-165
 MRT_HD float perlin_noise(const SceneView &sc, V3 p) {

@@ -16,7 +16,7 @@
  * sinf cosf atan2f asinf logf powf(.,5) are the correctly rounded values (double evaluation rounded once,
  * see miniraytracer_b200/csrc/mrt_libm.h for the rationale).
  *
- * usage: mrt_oracle -dump scene.txt -width W -height H -samples N -depth D -seed X [-s0 a -s1 b]
+ * usage: mrt_oracle -dump scene.txt -width W -height H -samples N -depth D -seed X [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d]
  *                   [-sky 0|1] [-image earthmap.ppm] [-threads T] -out acc.bin
  */
 #define _GNU_SOURCE
@@ -574,14 +574,14 @@ static void parse_scene(const char *path, Scene *sc) {
 
 /* ------------------------------------------------------------------ render driver */
 typedef struct { char magic[8]; uint32_t width, height, samples, s0, s1, depth, scene, threads; uint64_t seed, rays; double seconds; } FileHeader;
-static Scene g_scene; static uint32_t W = 500, H = 500, N = 16, S0 = 0, S1 = 0, SQ = 4; static uint64_t SEED = 11350390909718046443ULL;
+static Scene g_scene; static uint32_t W = 500, H = 500, N = 16, S0 = 0, S1 = 0, SQ = 4, X0 = 0, X1 = 0, Y0 = 0, Y1 = 0;   /* [X0,X1)x[Y0,Y1): crop window */ static uint64_t SEED = 11350390909718046443ULL;
 static float *g_acc; static uint32_t g_next_row; static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER; static uint64_t g_rays;
 static void *worker(void *arg) {
     (void) arg; Stats st = {0};
     for (;;) {
         pthread_mutex_lock(&g_lock); uint32_t y = g_next_row++; pthread_mutex_unlock(&g_lock);
-        if (y >= H) break;
-        for (uint32_t x = 0; x < W; x++) {
+        if (y >= Y1) break;
+        for (uint32_t x = X0; x < X1; x++) {
             V3 color = v3(0, 0, 0); uint32_t cnt = 0;
             for (uint32_t s = S0; s < S1; s++) {
                 Rng rng; pcg32_seed(&rng, SEED, ((uint64_t) y * W + x) * N + s);
@@ -592,7 +592,7 @@ static void *worker(void *arg) {
                 V3 c = trace(&g_scene, &r, 0, &rng, &st);
                 if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z)) { color = add(color, c); cnt++; }   /* main.cpp:163-165 */
             }
-            float *o = &g_acc[((size_t) y * W + x) * 4];
+            float *o = &g_acc[((size_t) (y - Y0) * (X1 - X0) + (x - X0)) * 4];
             o[0] = color.x; o[1] = color.y; o[2] = color.z; o[3] = (float) cnt;
         }
     }
@@ -614,6 +614,12 @@ int main(int argc, char **argv) {
     SQ = (uint32_t) sqrtf((float) spp); N = SQ * SQ;
     S0 = (uint32_t) atoi(arg(argc, argv, "-s0", "0")); S1 = (uint32_t) atoi(arg(argc, argv, "-s1", "0"));
     if (S1 == 0 || S1 > N) S1 = N;
+    X0 = (uint32_t) atoi(arg(argc, argv, "-x0", "0")); X1 = (uint32_t) atoi(arg(argc, argv, "-x1", "0"));
+    Y0 = (uint32_t) atoi(arg(argc, argv, "-y0", "0")); Y1 = (uint32_t) atoi(arg(argc, argv, "-y1", "0"));
+    if (X1 == 0 || X1 > W) X1 = W;
+    if (Y1 == 0 || Y1 > H) Y1 = H;
+    if (X0 >= X1 || Y0 >= Y1) { fprintf(stderr, "bad crop window\n"); return 2; }
+    g_next_row = Y0;
     if (image) {
         FILE *f = fopen(image, "rb"); int maxv;
         if (!f || fscanf(f, "P6 %d %d %d", &g_img_w, &g_img_h, &maxv) != 3) { fprintf(stderr, "bad ppm %s\n", image); return 1; }
@@ -624,16 +630,16 @@ int main(int argc, char **argv) {
     perlin_init();
     parse_scene(dump, &g_scene);
     g_scene.sky = atoi(arg(argc, argv, "-sky", "0"));
-    g_acc = calloc((size_t) W * H * 4, sizeof(float));
+    g_acc = calloc((size_t) (X1 - X0) * (Y1 - Y0) * 4, sizeof(float));
     pthread_t th[256]; if (threads > 256) threads = 256; if (threads < 1) threads = 1;
     for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, worker, NULL);
     for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
-    printf("{\"mode\":\"restatement\",\"rays\":%llu,\"paths\":%llu}\n", (unsigned long long) g_rays, (unsigned long long) W * H * (S1 - S0));
+    printf("{\"mode\":\"restatement\",\"rays\":%llu,\"paths\":%llu}\n", (unsigned long long) g_rays, (unsigned long long) (X1 - X0) * (Y1 - Y0) * (S1 - S0));
     if (out) {
         FileHeader h; memset(&h, 0, sizeof(h)); memcpy(h.magic, "MRTACC1", 8);
-        h.width = W; h.height = H; h.samples = N; h.s0 = S0; h.s1 = S1; h.depth = g_max_bounces; h.threads = (uint32_t) threads; h.seed = SEED; h.rays = g_rays;
+        h.width = X1 - X0; h.height = Y1 - Y0; h.samples = N; h.s0 = S0; h.s1 = S1; h.depth = g_max_bounces; h.threads = (uint32_t) threads; h.seed = SEED; h.rays = g_rays;
         FILE *f = fopen(out, "wb"); if (!f) { perror(out); return 1; }
-        fwrite(&h, sizeof(h), 1, f); fwrite(g_acc, sizeof(float) * 4, (size_t) W * H, f); fclose(f);
+        fwrite(&h, sizeof(h), 1, f); fwrite(g_acc, sizeof(float) * 4, (size_t) (X1 - X0) * (Y1 - Y0), f); fclose(f);
     }
     return 0;
 }

@@ -19,7 +19,9 @@
 //
 // usage:
 //   mrt_ref render -scene S -width W -height H -samples N -depth D -seed X
-//                  [-s0 a -s1 b] [-threads T] [-maxlum L] -out file.bin
+//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] -out file.bin
+//                  (crop window: only those pixels of the W x H frame are traced; stream ids and u,v stay the
+//                   full frame's, so BASELINE.json's full-size configurations can be spot-checked in seconds)
 //   mrt_ref stock  <reference command line>  [-dump file.bin]
 //   mrt_ref dump-scene -scene S -width W -height H -out file.txt
 //   mrt_ref kat
@@ -272,16 +274,23 @@ static int cmd_render(int argc, char **argv) {
     uint32 s1 = strtoul(argval(argc, argv, "-s1", "0"), 0, 0);
     if (s1 == 0 || s1 > N) s1 = N;
 
-    std::vector<float> acc((size_t) W * H * 4, 0.0f);
-    std::atomic<uint32> nextRow(0);
+    uint32 x0 = strtoul(argval(argc, argv, "-x0", "0"), 0, 0), x1 = strtoul(argval(argc, argv, "-x1", "0"), 0, 0);
+    uint32 y0 = strtoul(argval(argc, argv, "-y0", "0"), 0, 0), y1 = strtoul(argval(argc, argv, "-y1", "0"), 0, 0);
+    if (!x1 || x1 > W) x1 = W;
+    if (!y1 || y1 > H) y1 = H;
+    if (x0 >= x1 || y0 >= y1) { fprintf(stderr, "bad crop window\n"); return 2; }
+    const uint32 CW = x1 - x0, CH = y1 - y0;
+
+    std::vector<float> acc((size_t) CW * CH * 4, 0.0f);
+    std::atomic<uint32> nextRow(y0);
     G_rayCounter = 0;
 
     uint64 t0 = MRT_GetTime();
     auto worker = [&]() {
         for (;;) {
             uint32 y = nextRow.fetch_add(1);
-            if (y >= H) break;
-            for (uint32 x = 0; x < W; x++) {
+            if (y >= y1) break;
+            for (uint32 x = x0; x < x1; x++) {
                 Vec3 color(0, 0, 0);
                 uint32 cnt = 0;
                 for (uint32 s = s0; s < s1; s++) {
@@ -296,7 +305,7 @@ static int cmd_render(int argc, char **argv) {
                         cnt++;
                     }
                 }
-                float *o = &acc[((size_t) y * W + x) * 4];
+                float *o = &acc[((size_t) (y - y0) * CW + (x - x0)) * 4];
                 o[0] = color.r; o[1] = color.g; o[2] = color.b; o[3] = (float) cnt;
             }
         }
@@ -307,7 +316,7 @@ static int cmd_render(int argc, char **argv) {
     double secs = (MRT_GetTime() - t0) / 1e9;
 
     uint64 rays = G_rayCounter;
-    double paths = (double) W * H * (s1 - s0);
+    double paths = (double) CW * CH * (s1 - s0);
     printf("{\"mode\":\"render\",\"scene\":%u,\"width\":%u,\"height\":%u,\"samples\":%u,\"s0\":%u,\"s1\":%u,"
            "\"depth\":%u,\"threads\":%u,\"seconds\":%.6f,\"rays\":%llu,\"paths\":%.0f,"
            "\"mrays_per_s\":%.4f,\"mpaths_per_s\":%.4f}\n",
@@ -318,7 +327,7 @@ static int cmd_render(int argc, char **argv) {
         FileHeader h;
         memset(&h, 0, sizeof(h));
         memcpy(h.magic, "MRTACC1", 8);
-        h.width = W; h.height = H; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = p.maxBounces;
+        h.width = CW; h.height = CH; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = p.maxBounces;
         h.scene = p.sceneSelect; h.threads = nthreads; h.seed = seed; h.rays = rays; h.seconds = secs;
         return write_acc(out, h, acc.data());
     }

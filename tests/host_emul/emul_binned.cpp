@@ -3,7 +3,7 @@
 // check the warp scheduling logic -- ticket queue, bins, path pool, sample staging, chunk epilogue -- against the oracle.
 //
 // usage: emul_binned -scene S -width W -height H -samples N [-depth D] [-seed X] [-s0 a -s1 b] [-chunk K] [-bins B]
-//                    [-mode B|W|P] -assets DIR -out file.bin        (W / P: the pool-less kernels of the same header)
+//                    [-x0 a -x1 b -y0 c -y1 d] [-mode B|W|P] -assets DIR -out file.bin        (W / P: the pool-less kernels of the same header)
 #include "emul_warp.h"
 
 #include <cmath>
@@ -62,7 +62,13 @@ int main(int argc, char **argv) {
     uint32_t N = sq * sq;
     uint32_t s0 = strtoul(argval(argc, argv, "-s0", "0"), 0, 0), s1 = strtoul(argval(argc, argv, "-s1", "0"), 0, 0);
     if (s1 == 0 || s1 > N) s1 = N;
-    const uint32_t ns = s1 - s0, n_pixels = W * H;
+    uint32_t x0 = strtoul(argval(argc, argv, "-x0", "0"), 0, 0), x1 = strtoul(argval(argc, argv, "-x1", "0"), 0, 0);
+    uint32_t y0 = strtoul(argval(argc, argv, "-y0", "0"), 0, 0), y1 = strtoul(argval(argc, argv, "-y1", "0"), 0, 0);
+    if (!x1) x1 = W;
+    if (!y1) y1 = H;
+    const uint32_t CW = x1 - x0, CH = y1 - y0;
+    const uint32_t ns = s1 - s0, n_pixels = CW * CH;
+    a.crop_x0 = x0; a.crop_y0 = y0; a.crop_w = CW; a.n_pixels = n_pixels;
     a.width = W; a.height = H; a.sqrt_n = sq; a.s_begin = s0; a.s_end = s1; a.max_bounces = depth; a.seed = seed;
     a.accumulate = 0;
     a.stack_words = d.stack_words ? d.stack_words : 64;
@@ -105,7 +111,7 @@ int main(int argc, char **argv) {
         FileHeader h;
         memset(&h, 0, sizeof(h));
         memcpy(h.magic, "MRTACC1", 8);
-        h.width = W; h.height = H; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = depth; h.scene = scene; h.threads = 1;
+        h.width = CW; h.height = CH; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = depth; h.scene = scene; h.threads = 1;
         h.seed = seed; h.rays = counters[0]; h.seconds = 0;
         fwrite(&h, sizeof(h), 1, f);
         fwrite(acc.data(), sizeof(float4), acc.size(), f);

@@ -4,7 +4,7 @@
 // only by the test-suite; the shipped library has no CPU execution path.
 //
 // usage: emul_render -scene S -width W -height H -samples N -depth D -seed X
-//                    [-s0 a -s1 b] [-threads T] -assets DIR -out file.bin [-counters]
+//                    [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] -assets DIR -out file.bin [-counters] [-nocull]
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -45,13 +45,14 @@ int main(int argc, char **argv) {
     std::string assets = argval(argc, argv, "-assets", "assets");
     const char *out = argval(argc, argv, "-out", nullptr);
     bool want_counters = argflag(argc, argv, "-counters");
-    bool stepper = argflag(argc, argv, "-stepper");
-    const bool lite = argflag(argc, argv, "-specialised");   // run with the scene's own feature mask instead of MRT_FEAT_ALL   // incremental traversal (trav_step) instead of intersect()
+    const bool lite = argflag(argc, argv, "-specialised");   // run with the scene's own feature mask instead of MRT_FEAT_ALL
+    FlattenOptions fopt;
+    fopt.cull_boxes = !argflag(argc, argv, "-nocull");       // A/B of the translate cull boxes (must not change a bit)
 
     SceneGraph g;
     if (!build_scene(g, scene, float(W) / float(H), assets)) { fprintf(stderr, "scene: %s\n", g.error.c_str()); return 1; }
     FlatScene fs;
-    if (!flatten_scene(g, &fs)) { fprintf(stderr, "flatten: %s\n", fs.error.c_str()); return 1; }
+    if (!flatten_scene(g, &fs, fopt)) { fprintf(stderr, "flatten: %s\n", fs.error.c_str()); return 1; }
     const MrtSceneDesc &d = fs.desc;
     const uint32_t feat = lite ? (d.features ? d.features : MRT_FEAT_ALL) : MRT_FEAT_ALL;
     SceneView sv;
@@ -66,8 +67,14 @@ int main(int argc, char **argv) {
     uint32_t s1 = strtoul(argval(argc, argv, "-s1", "0"), 0, 0);
     if (s1 == 0 || s1 > N) s1 = N;
 
-    std::vector<float> acc((size_t) W * H * 4, 0.0f);
-    std::atomic<uint32_t> nextRow(0);
+    // crop window: pixels [x0,x1) x [y0,y1) of the W x H frame (stream ids and u,v stay those of the full frame)
+    uint32_t x0 = strtoul(argval(argc, argv, "-x0", "0"), 0, 0), x1 = strtoul(argval(argc, argv, "-x1", "0"), 0, 0);
+    uint32_t y0 = strtoul(argval(argc, argv, "-y0", "0"), 0, 0), y1 = strtoul(argval(argc, argv, "-y1", "0"), 0, 0);
+    if (!x1) x1 = W;
+    if (!y1) y1 = H;
+    const uint32_t CW = x1 - x0, CH = y1 - y0;
+    std::vector<float> acc((size_t) CW * CH * 4, 0.0f);
+    std::atomic<uint32_t> nextRow(y0);
     std::atomic<unsigned long long> rays(0);
     Counters total;
     memset(&total, 0, sizeof(total));
@@ -78,8 +85,8 @@ int main(int argc, char **argv) {
         memset(&cnt, 0, sizeof(cnt));
         for (;;) {
             uint32_t y = nextRow.fetch_add(1);
-            if (y >= H) break;
-            for (uint32_t x = 0; x < W; x++) {
+            if (y >= y1) break;
+            for (uint32_t x = x0; x < x1; x++) {
                 V3 color = v3(0, 0, 0);
                 uint32_t n_ok = 0;
                 for (uint32_t s = s0; s < s1; s++) {
@@ -93,14 +100,7 @@ int main(int argc, char **argv) {
                         Stack st;
                         st.base = stack_mem.data(); st.stride = 1; st.sp = 0;
                         bool hit;
-                        if (stepper) {
-                            Trav tr;
-                            trav_begin(sv, tr, 0.001f, FLT_MAX, st);
-                            while (trav_active(tr, st)) trav_step(sv, tr, p.ray, rec, rng, st, want_counters ? &cnt : nullptr);
-                            hit = trav_hit(tr);
-                        } else {
-                            hit = intersect(feat, sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
-                        }
+                        hit = intersect(feat, sv, p.ray, 0.001f, FLT_MAX, rec, rng, st, want_counters ? &cnt : nullptr);
                         if (st.sp != 0) { fprintf(stderr, "stack imbalance\n"); abort(); }
                         if (!path_shade(feat, sv, p, hit, rec, depth, rng)) break;
                     }
@@ -109,7 +109,7 @@ int main(int argc, char **argv) {
                         n_ok++;
                     }
                 }
-                float *o = &acc[((size_t) y * W + x) * 4];
+                float *o = &acc[((size_t) (y - y0) * CW + (x - x0)) * 4];
                 o[0] = color.x; o[1] = color.y; o[2] = color.z; o[3] = (float) n_ok;
             }
         }
@@ -129,12 +129,12 @@ int main(int argc, char **argv) {
         FileHeader h;
         memset(&h, 0, sizeof(h));
         memcpy(h.magic, "MRTACC1", 8);
-        h.width = W; h.height = H; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = depth; h.scene = scene; h.threads = nthreads;
+        h.width = CW; h.height = CH; h.samples = N; h.s0 = s0; h.s1 = s1; h.depth = depth; h.scene = scene; h.threads = nthreads;
         h.seed = seed; h.rays = total.rays;
         FILE *f = fopen(out, "wb");
         if (!f) { perror(out); return 1; }
         fwrite(&h, sizeof(h), 1, f);
-        fwrite(acc.data(), sizeof(float) * 4, (size_t) W * H, f);
+        fwrite(acc.data(), sizeof(float) * 4, (size_t) CW * CH, f);
         fclose(f);
     }
     return 0;

@@ -34,17 +34,19 @@ def ref_run(args, **kw):
     return subprocess.run([REF_BIN] + [str(a) for a in args], cwd=RUN_DIR, check=True, capture_output=True, text=True, **kw)
 
 
-def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0):
-    """Oracle render with per-(pixel, sample) RNG streams; returns (acc[h,w,4], meta). Cached in /tmp."""
+def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0, crop=None):
+    """Oracle render with per-(pixel, sample) RNG streams; returns (acc[h,w,4], meta). Cached in /tmp.
+    crop = (x0, y0, x1, y1): only that window of the frame (stream ids and u,v stay the full frame's)."""
     from miniraytracer_b200.accfile import read_acc
     os.makedirs(CACHE, exist_ok=True)
     st = os.stat(REF_BIN)
-    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
+    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{crop}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
     path = os.path.join(CACHE, f"ref_{key}.bin")
     if not os.path.exists(path):
         tmp = path + f".{os.getpid()}.tmp"
         ref_run(["render", "-scene", scene, "-width", width, "-height", height, "-samples", spp, "-depth", depth,
-                 "-seed", seed, "-s0", s0, "-s1", s1, "-threads", threads, "-out", tmp])
+                 "-seed", seed, "-s0", s0, "-s1", s1, "-threads", threads, "-out", tmp] +
+                (["-x0", crop[0], "-y0", crop[1], "-x1", crop[2], "-y1", crop[3]] if crop else []))
         os.replace(tmp, path)
     return read_acc(path)
 
@@ -67,15 +69,16 @@ def build_emul():
     return exe
 
 
-def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, env=None):
+def emul_render(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, extra=(), crop=None):
     from miniraytracer_b200.accfile import read_acc
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         path = f.name
     try:
         r = subprocess.run([exe, "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(spp),
                             "-depth", str(depth), "-seed", str(seed), "-s0", str(s0), "-s1", str(s1), "-assets", ASSETS,
-                            "-out", path, "-counters"], check=True, capture_output=True, text=True,
-                           env=dict(os.environ, **env) if env else None)
+                            "-out", path, "-counters"] + list(extra) +
+                           (["-x0", str(crop[0]), "-y0", str(crop[1]), "-x1", str(crop[2]), "-y1", str(crop[3])] if crop else []),
+                           check=True, capture_output=True, text=True)
         acc, meta = read_acc(path)
         meta["counters"] = json.loads(r.stdout.strip().splitlines()[-1])
         return acc, meta
@@ -100,14 +103,15 @@ def build_emul_binned():
     return exe
 
 
-def emul_binned(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, mode="B", chunk=0, bins=2):
+def emul_binned(exe, scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, mode="B", chunk=0, bins=2, crop=None, extra=()):
     from miniraytracer_b200.accfile import read_acc
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         path = f.name
     try:
         r = subprocess.run([exe, "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(spp),
                             "-depth", str(depth), "-seed", str(seed), "-s0", str(s0), "-s1", str(s1), "-mode", mode,
-                            "-chunk", str(chunk), "-bins", str(bins), "-assets", ASSETS, "-out", path],
+                            "-chunk", str(chunk), "-bins", str(bins), "-assets", ASSETS, "-out", path] + list(extra) +
+                           (["-x0", str(crop[0]), "-y0", str(crop[1]), "-x1", str(crop[2]), "-y1", str(crop[3])] if crop else []),
                            check=True, capture_output=True, text=True)
         acc, meta = read_acc(path)
         meta["info"] = json.loads(r.stdout.strip().splitlines()[-1])

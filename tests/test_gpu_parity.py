@@ -18,9 +18,9 @@ REL_TOL = 1e-4          # per-pixel relative tolerance stated by north_star
 MIN_FRAC = 0.999        # fraction of pixels that must agree
 
 
-def _gpu_render(scene, w, h, spp, depth=32, seed=api.DEFAULT_SEED, **kw):
+def _gpu_render(scene, w, h, spp, depth=32, seed=api.DEFAULT_SEED, tuning=None, **kw):
     hs = api.HostScene(scene, w, h)
-    r = api.Renderer(hs, 0)
+    r = api.Renderer(hs, 0, tuning)
     try:
         r.render_async(w, h, spp, depth, seed, **kw)
         st = r.stats()
@@ -71,26 +71,24 @@ def test_config_parity_vs_oracle(name, scene, w, h, spp):
 
 @needs_ref
 @pytest.mark.parametrize("scene,w,h,spp", [(5, 240, 136, 64), (0, 200, 200, 36)])
-def test_pixel_per_warp_mode(scene, w, h, spp, monkeypatch):
-    # MRT_BINNED=0 with >= 32 samples per launch selects the plain pixel-per-warp kernel (mode W: lanes keep their
-    # paths, lane sums combined by a shuffle tree); the default for such launches is mode B (test below)
+def test_pixel_per_warp_mode(scene, w, h, spp):
+    # MrtTuning.mode = MRT_MODE_PER_WARP selects the plain pixel-per-warp kernel (mode W: lanes keep their paths, lane
+    # sums combined by a shuffle tree); the default is mode B (test below)
     ref, meta = oracle_util.ref_render(scene, w, h, spp)
-    monkeypatch.setenv("MRT_BINNED", "0")
-    acc, st = _gpu_render(scene, w, h, spp)
-    assert st["mode"] == 1
+    acc, st = _gpu_render(scene, w, h, spp, tuning=dict(mode=api.MODE_PER_WARP))
+    assert st["mode"] == api.MODE_PER_WARP
     _check(acc, ref, meta["rays"], st)
 
 
-@pytest.mark.parametrize("binned,slice_mode", [("0", 0), (None, 3)])
-def test_modes_and_slices_agree(binned, slice_mode, monkeypatch):
-    # 64 spp in one launch == four accumulated 16-sample slices; with MRT_BINNED=0 the slices run the pixel-per-lane
-    # kernel (mode P), by default mode B takes any sample count
-    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)
-    else: monkeypatch.setenv("MRT_BINNED", binned)
+@pytest.mark.parametrize("mode", [api.MODE_PER_LANE, api.MODE_BINNED])
+def test_modes_and_slices_agree(mode):
+    # 64 spp in one launch == four accumulated 16-sample slices, in the pixel-per-lane kernel (mode P) and in mode B
+    slice_mode = mode
+    tuning = dict(mode=mode)
     w, h, spp = 160, 90, 64
-    full, st = _gpu_render(5, w, h, spp)
+    full, st = _gpu_render(5, w, h, spp, tuning=tuning)
     hs = api.HostScene(5, w, h)
-    r = api.Renderer(hs, 0)
+    r = api.Renderer(hs, 0, tuning)
     for i in range(4):
         r.render_async(w, h, spp, sample_begin=16 * i, sample_end=16 * (i + 1), accumulate=(i > 0))
         assert r.stats()["mode"] == slice_mode
@@ -174,31 +172,18 @@ def test_poll_and_cancel():
 
 
 @needs_ref
-@pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 36), (7, 160, 90, 16), (8, 128, 72, 16)])
-def test_wavefront_renderer_parity(scene, w, h, spp, monkeypatch):
-    """The opt-in wavefront renderer (MRT_WAVEFRONT=1: wf_logic + persistent incremental wf_trav) computes the
-    same accumulators as the megakernel -- it runs the same per-path phases of trace_core.h."""
-    ref, meta = oracle_util.ref_render(scene, w, h, spp)
-    monkeypatch.setenv("MRT_WAVEFRONT", "1")
-    acc, st = _gpu_render(scene, w, h, spp)
-    assert st["mode"] == 2
-    _check(acc, ref, meta["rays"], st)
-
-
-@needs_ref
 @pytest.mark.parametrize("binned", [None, 1, 2, 3])
 @pytest.mark.parametrize("scene,w,h,spp", [(5, 160, 90, 64), (6, 128, 72, 36), (7, 96, 54, 36), (8, 96, 54, 36), (0, 96, 96, 49)])
-def test_binned_pool_renderer_parity(scene, w, h, spp, binned, monkeypatch):
-    """Mode B (MRT_BINNED: paths parked in a per-warp pool and regrouped by a ray classifier between segments)
-    runs the same per-path arithmetic as the other modes: same ray count, accumulators equal up to the order of
-    the per-pixel sum."""
+def test_binned_pool_renderer_parity(scene, w, h, spp, binned):
+    """Mode B (paths parked in a per-warp pool and regrouped by a ray classifier between segments; MrtTuning.bins: one bin,
+    classifier bins, + pending-weight bit) runs the same per-path arithmetic as the other modes: same ray count,
+    accumulators equal up to the order of the per-pixel sum."""
     ref, meta = oracle_util.ref_render(scene, w, h, spp)
-    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)   # the default
-    else: monkeypatch.setenv("MRT_BINNED", str(binned))
-    acc, st = _gpu_render(scene, w, h, spp)
-    assert st["mode"] == 3
+    tuning = None if binned is None else dict(bins=binned)   # None: the default
+    acc, st = _gpu_render(scene, w, h, spp, tuning=tuning)
+    assert st["mode"] == api.MODE_BINNED
     _check(acc, ref, meta["rays"], st)
-    acc2, _ = _gpu_render(scene, w, h, spp)
+    acc2, _ = _gpu_render(scene, w, h, spp, tuning=tuning)
     assert np.array_equal(acc, acc2), "binned schedule must be reproducible run to run"
 
 
@@ -230,18 +215,13 @@ def test_progressive_passes_single_gpu():
     assert res["n_bad"] == 0, res
 
 
-def test_binned_result_does_not_depend_on_the_schedule(monkeypatch):
+def test_binned_result_does_not_depend_on_the_schedule():
     """Mode B sums the finished samples of a pixel in item order from its staging array, so the accumulator is
     bit-identical whatever the bins, the chunk size or the launch bounds (i.e. whichever lane ran which path)."""
     ref = None
-    for env in ({"MRT_BINNED": "1"}, {"MRT_BINNED": "2"}, {"MRT_BINNED": "3"}, {"MRT_BINNED": "2", "MRT_CHUNK": "3"},
-                {"MRT_BINNED": "2", "MRT_MINB": "8"}):
-        for k in ("MRT_BINNED", "MRT_CHUNK", "MRT_MINB"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        acc, st = _gpu_render(6, 128, 72, 64)
-        assert st["mode"] == 3
+    for tuning in (dict(bins=1), dict(bins=2), dict(bins=3), dict(bins=2, chunk_pixels=3), dict(bins=2, min_blocks=8)):
+        acc, st = _gpu_render(6, 128, 72, 64, tuning=tuning)
+        assert st["mode"] == api.MODE_BINNED
         if ref is None: ref = acc
         else: np.testing.assert_array_equal(acc, ref)
 
@@ -249,9 +229,9 @@ def test_binned_result_does_not_depend_on_the_schedule(monkeypatch):
 def test_deep_paths_fall_back_to_mode_w():
     """A bounce limit above 255 does not fit the parked path's 8-bit depth field: such launches use mode W."""
     acc, st = _gpu_render(5, 96, 54, 36, depth=300)
-    assert st["mode"] == 1
+    assert st["mode"] == api.MODE_PER_WARP
     ref, st2 = _gpu_render(5, 96, 54, 36, depth=255)
-    assert st2["mode"] == 3
+    assert st2["mode"] == api.MODE_BINNED
     # in the Cornell box paths practically never reach 255 bounces, so the two images agree sample for sample
     np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
     res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-4)
@@ -259,18 +239,70 @@ def test_deep_paths_fall_back_to_mode_w():
 
 
 @needs_ref
-@pytest.mark.parametrize("binned", [None, "0"])
-def test_ragged_frames_and_slices_vs_oracle(binned, monkeypatch):
+@pytest.mark.parametrize("mode", [api.MODE_AUTO, api.MODE_PER_WARP, api.MODE_PER_LANE])
+def test_ragged_frames_and_slices_vs_oracle(mode):
     """Edge shapes against the oracle in mode B (default) and modes W / P: fewer pixels than lanes, sample counts that
     are not multiples of 32, a sample slice that starts and ends inside the grid, a scene with a BVH."""
-    if binned is None: monkeypatch.delenv("MRT_BINNED", raising=False)
-    else: monkeypatch.setenv("MRT_BINNED", binned)
     for scene, w, h, spp, s0, s1 in [(5, 7, 3, 1, 0, 1), (5, 33, 5, 4, 0, 4), (6, 5, 1, 49, 0, 49), (0, 31, 9, 36, 0, 36),
                                       (5, 40, 22, 16, 5, 12), (8, 24, 13, 100, 37, 90)]:
         ref, meta = oracle_util.ref_render(scene, w, h, spp, s0=s0, s1=s1)
-        acc, st = _gpu_render(scene, w, h, spp, sample_begin=s0, sample_end=s1)
+        acc, st = _gpu_render(scene, w, h, spp, sample_begin=s0, sample_end=s1, tuning=dict(mode=mode))
         assert st["paths"] == w * h * (s1 - s0)
         assert st["rays"] == meta["rays"], (scene, w, h, spp, st["rays"], meta["rays"])
         np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
         res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=REL_TOL)
         assert res["n_bad"] == 0, (scene, w, h, spp, res)
+
+
+# ---- parity at BASELINE.json's TRUE configuration sizes, through crop windows (the oracle traces only the window; PCG32
+# stream ids ((y*W+x)*N+s, pcg.cpp:28-35, main.cpp:156-157) and sub-pixel positions are those of the full frame).  C4 and C5
+# have stream ids above 2^32 (2^34.9 in the C5_upper window; the frame's corners are outside the Cornell box, i.e. black).  Golden windows are committed
+# (tests/golden/make_golden_windows.py), so this also runs where the oracle binary is absent.
+WINDOWS = [
+    # name, scene, W, H, spp, (x0, y0, x1, y1)
+    ("C2_center", 5, 1920, 1080, 1024, (928, 508, 992, 572)),
+    ("C2_upper", 5, 1920, 1080, 1024, (1300, 1000, 1364, 1064)),
+    ("C3_smoke", 6, 1920, 1080, 1024, (640, 300, 704, 364)),
+    ("C4_upper", 7, 1920, 1080, 4096, (560, 790, 624, 854)),         # stream ids up to 2^32.6
+    ("C4_spheres", 7, 1920, 1080, 4096, (1100, 640, 1164, 704)),
+    ("C5_upper", 8, 3840, 2160, 4096, (1888, 2030, 1952, 2094)),      # stream ids up to 2^34.94 (the corners of the frame see nothing)
+    ("C5_bunny", 8, 3840, 2160, 4096, (1480, 900, 1544, 964)),
+    ("C1_rows", 0, 500, 500, 16, (0, 236, 500, 264)),
+]
+
+
+@pytest.mark.parametrize("name,scene,W,H,spp,crop", WINDOWS)
+def test_true_size_window_parity(name, scene, W, H, spp, crop):
+    g = np.load(os.path.join(GOLDEN, f"window_{name}.npz"))
+    assert (int(g["width"]), int(g["height"]), int(g["spp"])) == (W, H, spp) and tuple(int(v) for v in g["crop"]) == crop
+    hs = api.HostScene(scene, W, H)
+    r = api.Renderer(hs, 0)
+    try:
+        r.render_async(W, H, spp, crop=crop)
+        st = r.stats()
+        acc = r.readback()
+    finally:
+        r.close(); hs.close()
+    x0, y0, x1, y1 = crop
+    assert acc.shape == (y1 - y0, x1 - x0, 4)
+    assert st["paths"] == (x1 - x0) * (y1 - y0) * spp
+    # identical streams: the trace() call count is equal up to rare ulp-flipped decisions, >= 99.9 % of the window's pixels
+    # within 1e-4 (a window has few pixels but 1024-4096 samples each, so a single flipped path moves a pixel by < 1e-3)
+    assert abs(int(st["rays"]) - int(g["rays"])) <= 2e-4 * int(g["rays"]), (st["rays"], int(g["rays"]))
+    np.testing.assert_array_equal(acc[..., 3], g["acc"][..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(g["acc"]), rel=REL_TOL)
+    assert res["frac_ok"] >= MIN_FRAC, res
+
+
+@needs_ref
+def test_crop_window_equals_full_frame():
+    """A window is bit-identical to the same pixels of a full render (same streams, same per-pixel sum order)."""
+    w, h, spp = 96, 54, 36
+    full, _ = _gpu_render(7, w, h, spp)
+    crop = (40, 10, 77, 31)
+    part, st = _gpu_render(7, w, h, spp, crop=crop)
+    np.testing.assert_array_equal(part, full[10:31, 40:77])
+    ref, meta = oracle_util.ref_render(7, w, h, spp, crop=crop)
+    assert st["rays"] == meta["rays"]
+    with pytest.raises(api.MrtError):
+        _gpu_render(7, w, h, spp, crop=(10, 10, 10, 20))

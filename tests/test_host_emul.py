@@ -60,7 +60,25 @@ def test_translate_cull_box_is_conservative(emul_bin, scene, w, h, spp):
     rays that miss it (trace_core.h: cull_miss).  The reference tests nothing there, so the cull must never change a
     result: with and without it the accumulators are bit-identical, and fewer transforms are entered."""
     a, ma = oracle_util.emul_render(emul_bin, scene, w, h, spp)
-    b, mb = oracle_util.emul_render(emul_bin, scene, w, h, spp, env={"MRT_NO_CULL": "1"})
+    b, mb = oracle_util.emul_render(emul_bin, scene, w, h, spp, extra=["-nocull"])
     assert ma["rays"] == mb["rays"]
     np.testing.assert_array_equal(a, b)
     assert ma["counters"]["xform"] < mb["counters"]["xform"]
+
+
+# crop windows of the BASELINE configurations at their true sizes: PCG32 stream ids (y*W+x)*N+s above 2^32 (C4) and
+# 2^34 (C5) -- pcg.cpp:28-35, main.cpp:156-157 -- on a handful of pixels and a slice of the samples
+BIG_WINDOWS = [(8, 3840, 2160, 4096, (1900, 2040, 1906, 2042), 4000, 4024), (7, 1920, 1080, 4096, (1130, 660, 1136, 662), 100, 124),
+               (5, 1920, 1080, 1024, (950, 540, 956, 542), 1000, 1024)]
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp,crop,s0,s1", BIG_WINDOWS)
+def test_core_crop_window_at_true_config_size(emul_bin, scene, w, h, spp, crop, s0, s1):
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp, s0=s0, s1=s1, crop=crop)
+    acc, meta = oracle_util.emul_render(emul_bin, scene, w, h, spp, s0=s0, s1=s1, crop=crop)
+    assert acc.shape == (crop[3] - crop[1], crop[2] - crop[0], 4)
+    assert meta["rays"] == rmeta["rays"] and rmeta["rays"] > acc.shape[0] * acc.shape[1] * (s1 - s0)   # paths do bounce there
+    np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
+    assert res["n_bad"] == 0, res

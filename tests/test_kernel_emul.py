@@ -64,3 +64,13 @@ def test_mode_b_kernel_matches_golden_without_the_reference(emul_kernel_bin):
         pytest.skip("golden frame too large for the fiber emulation")
     acc, meta = oracle_util.emul_binned(emul_kernel_bin, 5, w, h, spp, depth=depth)
     _same(acc, g["acc"], meta["rays"], int(g["rays"]))
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp,crop,s0,s1", [(8, 3840, 2160, 4096, (1900, 2040, 1906, 2042), 4000, 4024),
+                                                        (7, 1920, 1080, 4096, (1130, 660, 1136, 662), 100, 124)])
+def test_mode_b_crop_window_at_true_config_size(emul_kernel_bin, scene, w, h, spp, crop, s0, s1):
+    """The kernels' crop window (MrtRenderParams.crop_*): window pixel -> frame (x, y) -> stream id above 2^32 / 2^34."""
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp, s0=s0, s1=s1, crop=crop)
+    acc, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, s0=s0, s1=s1, crop=crop)
+    _same(acc, ref, meta["rays"], rmeta["rays"])

@@ -55,6 +55,18 @@ def test_restatement_sample_slices_and_depth(restatement, tmp_path):
     np.testing.assert_array_equal(acc, ref)
 
 
+@pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+def test_restatement_crop_window_with_large_stream_ids(restatement, tmp_path):
+    """Crop window of C5's true frame (3840x2160, 4096 spp): stream ids (y*W+x)*N+s near 2^35."""
+    dump = str(tmp_path / "scene.txt")
+    oracle_util.ref_dump_scene(8, 3840, 2160, dump)
+    crop = (1900, 2040, 1906, 2042)
+    ref, rmeta = oracle_util.ref_render(8, 3840, 2160, 4096, s0=4000, s1=4024, crop=crop)
+    acc, meta = _run(restatement, dump, 3840, 2160, 4096, 0, extra=("-s0", "4000", "-s1", "4024", "-x0", "1900", "-y0", "2040", "-x1", "1906", "-y1", "2042"))
+    assert meta["rays"] == rmeta["rays"]
+    np.testing.assert_array_equal(acc, ref)
+
+
 @pytest.mark.parametrize("scene", [2, 3, 5, 6])
 def test_restatement_on_committed_dumps(restatement, scene):
     """Runs without the reference binary: committed scene dumps (printed by the reference) + committed golden

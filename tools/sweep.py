@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Tuning sweep on a GPU box: kernel variants (MRT_MINB launch bounds, MRT_CHUNK pixels per warp task) x workloads.
+"""Tuning sweep on a GPU box: MrtTuning fields (launch bounds, chunk size, mode, bins, ...) x workloads.
 Prints one JSON line per measurement (kernel time from CUDA events on the launch stream, after a warm-up)."""
 import argparse
 import json
@@ -17,13 +17,11 @@ CASES = {
 }
 
 
-def measure(case, minb, chunk, reps=2, depth=32):
+def measure(case, tuning, reps=2, depth=32):
     reps = int(os.environ.get("MRT_SWEEP_REPS", reps))
     scene, w, h, spp = CASES[case]
-    os.environ["MRT_MINB"] = str(minb)
-    os.environ["MRT_CHUNK"] = str(chunk)
     hs = api.HostScene(scene, w, h)
-    r = api.Renderer(hs, 0)
+    r = api.Renderer(hs, 0, tuning)
     best = None
     for i in range(reps + 1):
         r.render_async(w, h, spp, depth=depth)
@@ -31,30 +29,23 @@ def measure(case, minb, chunk, reps=2, depth=32):
         if i > 0 and (best is None or st["kernel_ms"] < best["kernel_ms"]):
             best = st
     r.close(); hs.close()
-    return {"case": case, "minb": minb, "chunk": chunk, "kernel_ms": best["kernel_ms"], "grays_per_s": best["rays"] / best["kernel_ms"] / 1e6,
-            "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"],
-            "alive_frac": best["rays"] / max(1, 32 * best["warp_iterations"])}
+    res = {"case": case, "kernel_ms": best["kernel_ms"], "grays_per_s": best["rays"] / best["kernel_ms"] / 1e6,
+           "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"], "mode": best["mode"],
+           "alive_frac": best["rays"] / max(1, 32 * best["warp_iterations"]), "depth": depth}
+    res.update(tuning)
+    return res
 
 
 if __name__ == "__main__":
+    import itertools
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="C2")
-    ap.add_argument("--minb", default="5")
-    ap.add_argument("--chunk", default="0")
-    ap.add_argument("--wavefront", default="0")
-    ap.add_argument("--all", default="0", help="MRT_VARIANT_ALL values")
-    ap.add_argument("--order", default="0")
-    ap.add_argument("--binned", default="0", help="MRT_BINNED values (0 off, 1 pool, 2 +box bins, 3 +pending bit)")
     ap.add_argument("--depth", default="32", help="max bounces (comma list)")
+    fields = [n for n, _ in api.Tuning._fields_ if n != "reserved"]
+    for f in fields:   # every MrtTuning field as a comma list, e.g. --min_blocks 5,6 --coop_trees 1,2
+        ap.add_argument("--" + f, default="0")
     args = ap.parse_args()
-    import itertools
-    for case, minb, chunk, wf, pf, order in itertools.product(args.cases.split(","), args.minb.split(","), args.chunk.split(","),
-                                                             args.wavefront.split(","), args.all.split(","), args.order.split(",")):
-      for depth, binned in itertools.product(args.depth.split(","), args.binned.split(",")):
-        os.environ["MRT_BINNED"] = binned
-        os.environ["MRT_WAVEFRONT"] = wf
-        os.environ["MRT_VARIANT_ALL"] = pf
-        os.environ["MRT_ORDER"] = order
-        res = measure(case, int(minb), int(chunk), depth=int(depth))
-        res.update(wavefront=int(wf), variant_all=int(pf), order=int(order), depth=int(depth), binned=int(binned))
-        print(json.dumps(res), flush=True)
+    for case, depth in itertools.product(args.cases.split(","), args.depth.split(",")):
+        for combo in itertools.product(*[getattr(args, f).split(",") for f in fields]):
+            tuning = {f: int(v) for f, v in zip(fields, combo)}
+            print(json.dumps(measure(case, tuning, depth=int(depth))), flush=True)
