@@ -136,6 +136,10 @@ typedef struct MrtRenderStats {
     float kernel_ms;     /* CUDA-event time of the render kernel on its stream */
     uint32_t grid, block, smem_bytes;
     uint32_t mode;       /* MRT_MODE_* of the kernel that ran */
+    uint32_t coop_trees; /* 1 = BVH trees were traversed warp-cooperatively (coop_tree.cuh) */
+    /* cooperative traversal: steps executed (summed over warps) and work items popped in them: items / (32 * steps) =
+       lane fill of the node (box tests) and leaf (primitive tests) phases */
+    uint64_t coop_node_steps, coop_node_items, coop_leaf_steps, coop_leaf_items;
 } MrtRenderStats;
 /* Statistics of the last finished render (blocks like mrt_gpu_wait). */
 int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out);

@@ -126,7 +126,8 @@ typedef struct MrtSceneDesc {
     uint32_t sky;             /* 1: sky gradient on miss (sceneSelect < SCENE_CORNELL_BOX, main.cpp:110) */
     uint32_t stack_words;     /* worst-case traversal stack depth in 32-bit words (computed by the flattener) */
     uint32_t features;        /* MRT_FEAT_* mask of what the scene contains (0 is treated as MRT_FEAT_ALL) */
-    uint32_t reserved0;
+    uint32_t stack_words_coop; /* the same when BVH trees are traversed warp-cooperatively (the per-lane stack then holds no tree
+                                  frames); 0 = the scene's trees do not qualify (see coop_tree.cuh), per-lane traversal only */
     MrtCamera camera;
 
     const MrtF4 *sphere;  uint32_t n_sphere;

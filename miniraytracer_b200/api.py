@@ -24,7 +24,7 @@ class Camera(C.Structure):
 class SceneDesc(C.Structure):
     _fields_ = [
         ("root", C.c_uint32), ("n_lights", C.c_uint32), ("lights", C.POINTER(C.c_uint32)),
-        ("sky", C.c_uint32), ("stack_words", C.c_uint32), ("features", C.c_uint32), ("reserved0", C.c_uint32),
+        ("sky", C.c_uint32), ("stack_words", C.c_uint32), ("features", C.c_uint32), ("stack_words_coop", C.c_uint32),
         ("camera", Camera),
         ("sphere", C.POINTER(F4)), ("n_sphere", C.c_uint32),
         ("rect", C.POINTER(F4)), ("n_rect", C.c_uint32),
@@ -77,7 +77,8 @@ class DeviceInfo(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("nonfinite", C.c_uint64), ("warp_iterations", C.c_uint64), ("kernel_ms", C.c_float),
-                ("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32), ("mode", C.c_uint32)]
+                ("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32), ("mode", C.c_uint32), ("coop_trees", C.c_uint32),
+                ("coop_node_steps", C.c_uint64), ("coop_node_items", C.c_uint64), ("coop_leaf_steps", C.c_uint64), ("coop_leaf_items", C.c_uint64)]
 
 
 MRT_RENDER_ACCUMULATE = 1

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <vector>
 
 #include "scene_graph.h"
 
@@ -293,26 +294,79 @@ struct Flattener {
         if (pn.prim_count) return 0;
         return 1 + std::max(pod_depth(m, pn.left), pod_depth(m, pn.left + 1));
     }
-    uint32_t depth_w(int id) const { return node_is_prim(id) ? 1u : depth(id); }   // wrapped primitives cost one LIST frame
-    uint32_t depth(int id) const {
+    // coop = true: BVH trees are traversed warp-cooperatively (coop_tree.cuh) and cost no per-lane stack frames
+    uint32_t depth_w(int id, bool coop) const { return node_is_prim(id) ? 1u : depth(id, coop); }   // wrapped primitives cost one LIST frame
+    uint32_t depth(int id, bool coop) const {
         const Node &n = g.nodes[id];
         switch (n.kind) {
         case NodeKind::List: {
             uint32_t d = 0;
-            for (int c : n.children) d = std::max(d, depth(c));
+            for (int c : n.children) d = std::max(d, depth(c, coop));
             return 1 + d;
         }
-        case NodeKind::Box: return depth(n.child);
-        case NodeKind::Bvh: return 1 + std::max(depth_w(n.left), depth_w(n.right));
+        case NodeKind::Box: return depth(n.child, coop);
+        case NodeKind::Bvh: return coop ? 0u : 1 + std::max(depth_w(n.left, coop), depth_w(n.right, coop));
         case NodeKind::Translate:
-        case NodeKind::RotateY: return 11 + depth_w(n.child);
-        case NodeKind::Volume: return 1 + depth_w(n.child);
-        case NodeKind::PodBvh: return pod_depth(g.meshes[n.mesh], 0);
+        case NodeKind::RotateY: return 11 + depth_w(n.child, coop);
+        case NodeKind::Volume: return 1 + depth_w(n.child, coop);
+        case NodeKind::PodBvh: return coop ? 0u : pod_depth(g.meshes[n.mesh], 0);
         default: return 0;
         }
     }
 };
 }  // namespace
+
+// Do the scene's BVH trees qualify for the warp-cooperative traversal (coop_tree.cuh)?  Every tree at most 31 levels deep
+// (the rank has one bit per level), every leaf a triangle leaf or an object_list of spheres / rects / lists of those
+// (what coop_leaf_hit evaluates), and no tree inside a constant_volume boundary (probe mode stays per-lane).
+// Works on the flattened tables, so it also covers scenes loaded from a file.
+bool coop_trees_supported(const MrtSceneDesc &d) {
+    auto u = [](float f) { uint32_t v; memcpy(&v, &f, 4); return v; };
+    auto list_ok = [&](uint32_t li, bool nested, auto &&self) -> bool {
+        if (li >= d.n_list) return false;
+        for (uint32_t ci = u(d.list[2 * li].w); ; ci++) {
+            if (ci >= d.n_child) return false;
+            const uint32_t c = d.child[ci], t = MRT_REF_TYPE(c);
+            if (t == MRT_T_END) return true;
+            if (t <= MRT_T_RECT_YZ) continue;
+            if (t == MRT_T_LIST && !nested && self(MRT_REF_INDEX(c), true, self)) continue;
+            return false;
+        }
+    };
+    struct Item { uint32_t ref, depth; };
+    std::vector<Item> todo;
+    for (uint32_t b = 0; b < d.n_bvh; b++) todo.push_back(Item{u(d.bvh[2 * b].w), 1});
+    size_t visited = 0;
+    while (!todo.empty()) {
+        Item it = todo.back(); todo.pop_back();
+        if (++visited > (size_t) d.n_node2 * 2 + d.n_bvh + 16) return false;   // not a tree
+        const uint32_t t = MRT_REF_TYPE(it.ref), i = MRT_REF_INDEX(it.ref);
+        if (t == MRT_T_NODE2) {
+            if (i >= d.n_node2 || it.depth > 31) return false;
+            todo.push_back(Item{u(d.node2[4 * i].w) & 0x0FFFFFFFu, it.depth + 1});
+            todo.push_back(Item{u(d.node2[4 * i + 1].w) & 0x0FFFFFFFu, it.depth + 1});
+        } else if (t == MRT_T_TRILEAF) {
+            if (i >= d.n_trileaf) return false;
+        } else if (t == MRT_T_LIST) {
+            if (!list_ok(i, false, list_ok)) return false;
+        } else return false;
+    }
+    // volumes: the boundary subtree must not contain a tree
+    std::vector<uint32_t> st;
+    for (uint32_t v = 0; v < d.n_vol; v++) st.push_back(u(d.vol[v].x));
+    visited = 0;
+    while (!st.empty()) {
+        const uint32_t r = st.back(); st.pop_back();
+        if (++visited > (size_t) d.n_child + d.n_list + d.n_xlate + d.n_rot + d.n_vol + 16) return false;
+        const uint32_t t = MRT_REF_TYPE(r), i = MRT_REF_INDEX(r);
+        if (t == MRT_T_BVH || t == MRT_T_NODE2 || t == MRT_T_TRILEAF) return false;
+        if (t == MRT_T_LIST && i < d.n_list) { for (uint32_t ci = u(d.list[2 * i].w); ci < d.n_child && MRT_REF_TYPE(d.child[ci]) != MRT_T_END; ci++) st.push_back(d.child[ci]); }
+        else if (t == MRT_T_TRANSLATE && i < d.n_xlate) st.push_back(u(d.xlate[3 * i].w));
+        else if (t == MRT_T_ROTATE_Y && i < d.n_rot) st.push_back(u(d.rot[3 * i].w));
+        else if (t == MRT_T_VOLUME && i < d.n_vol) st.push_back(u(d.vol[i].x));
+    }
+    return d.n_bvh > 0;
+}
 
 bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &opt) {
     FlatScene &o = *out;
@@ -367,7 +421,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &op
     d.n_lights = (uint32_t) o.lights.size();
     d.lights = o.lights.data();
     d.sky = g.sky ? 1u : 0u;
-    d.stack_words = fl.depth_w(g.objects) + 2;
+    d.stack_words = fl.depth_w(g.objects, false) + 2;
     {   // feature mask: what a specialised kernel must be able to handle
         uint32_t f = 0;
         if (!o.node2.empty() || !o.bvh.empty() || !o.trileaf.empty()) f |= MRT_FEAT_TREES;
@@ -406,6 +460,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &op
     d.perlin_perm = o.perlin_perm.empty() ? nullptr : o.perlin_perm.data();
     d.image = o.image.empty() ? nullptr : o.image.data();
     d.n_image_bytes = o.image.size();
+    d.stack_words_coop = coop_trees_supported(d) ? fl.depth_w(g.objects, true) + 2 : 0u;
     return true;
 }
 

@@ -27,7 +27,7 @@ struct MrtScene {
     int sm_count = 0;
     std::vector<void *> allocs;
     mrt::SceneView view;
-    uint32_t stack_words = 0;
+    uint32_t stack_words = 0, stack_words_coop = 0;
     MrtTuning tuning = {};        // mrt_gpu_set_tuning; all zero = measured defaults
     uint32_t has_trees = 0;
     uint32_t features = 0;        // MRT_FEAT_* mask of the scene -> kernel variant (render_variants.h)
@@ -53,6 +53,7 @@ struct MrtScene {
     bool rendered = false;
     MrtRenderParams last;
     uint32_t last_tasks = 0, last_grid = 0, last_block = mrt::kBlock, last_smem = 0, last_mode = 0;
+    bool last_coop = false;
     uint32_t last_w = 0, last_h = 0;   // size of the rendered window = of the accumulator
     float4 *last_acc = nullptr;
     // pixel work order (Z-curve), rebuilt when the frame size changes

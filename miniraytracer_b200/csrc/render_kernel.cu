@@ -328,7 +328,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
         s->allocs.push_back(base);
         if (cudaMemcpy(base, staging.data(), pk.total, cudaMemcpyHostToDevice) != cudaSuccess) { set_error(std::string("cudaMemcpy scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
         for (const Packer::Item &it : pk.items) *it.dev = base + it.offset;
-        s->counters = (unsigned long long *) (base + ctrl_off);          // 32 bytes
+        s->counters = (unsigned long long *) (base + ctrl_off);          // 8 x 8 bytes
         s->ticket = (unsigned int *) (base + ctrl_off + 64);
         s->max_bits = (unsigned int *) (base + ctrl_off + 128);
         s->cancel_dev = (int *) (base + ctrl_off + 192);
@@ -338,6 +338,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     v.sky = d->sky;
     v.cam = d->camera;
     s->stack_words = d->stack_words ? d->stack_words : 64;
+    s->stack_words_coop = d->stack_words_coop;   // 0: trees do not qualify for the warp-cooperative traversal
     s->has_trees = d->n_node2 ? 1u : 0u;
     s->features = d->features;
     find_classifier_boxes(d, s);
@@ -462,7 +463,6 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.s_begin = p->sample_begin; a.s_end = p->sample_end; a.max_bounces = p->max_bounces;
     a.seed = p->seed;
     a.accumulate = (p->flags & MRT_RENDER_ACCUMULATE) ? 1u : 0u;
-    a.stack_words = s->stack_words;
     a.acc = acc;
     a.ticket = s->ticket;
     a.counters = s->counters;
@@ -488,7 +488,12 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)
     int minb = tn.min_blocks ? (int) tn.min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
     const Variant *variant = tn.variant_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
-    const void *kernel = variant->get(binned ? 2 : (mode_w ? 1 : 0), minb);
+    // BVH trees: warp-cooperative traversal (coop_tree.cuh) in mode B where the scene's trees qualify
+    const bool coop_ok = binned && s->has_trees && s->stack_words_coop != 0u && (variant->mask & MRT_FEAT_TREES);
+    if (tn.coop_trees == 2u && !coop_ok) { set_error("mrt_gpu_render_async: cooperative tree traversal needs mode B and qualifying trees"); return MRT_E_INVALID; }
+    const bool coop = coop_ok && tn.coop_trees != 1u;
+    const void *kernel = variant->get(coop ? 3 : (binned ? 2 : (mode_w ? 1 : 0)), minb);
+    const uint32_t stack_words = coop ? s->stack_words_coop : s->stack_words;
     uint32_t n_bins = 1;
     a.pool = nullptr;
     a.stage = nullptr;
@@ -511,7 +516,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     int blocks_per_sm = 0;
     uint32_t resident_warps = 0;
     auto occupancy = [&](uint32_t k) -> int {
-        smem = (size_t) warps_per_block * s->stack_words * 32u * sizeof(uint32_t);
+        smem = (size_t) warps_per_block * stack_words * 32u * sizeof(uint32_t);
+        if (coop) smem += (size_t) warps_per_block * kCoopWords * sizeof(uint32_t);
         if (mode_w && !binned) smem += (size_t) warps_per_block * k * 32u * sizeof(float4);
         if (binned) smem += (size_t) warps_per_block * (n_bins + 1u) * kPoolCap;
         if (smem > 48 * 1024) {
@@ -562,6 +568,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         if (K < 32u) K = 32u;
         if (K > 1024u) K = 1024u;
     }
+    a.stack_words = stack_words;
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
     uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
@@ -587,7 +594,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     }
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     void *kargs[] = {(void *) &a};
     CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, s->stream));
@@ -599,6 +606,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     s->last_grid = grid;
     s->last_block = threads;
     s->last_smem = (uint32_t) smem;
+    s->last_coop = coop;
     s->last_mode = binned ? MRT_MODE_BINNED : (mode_w ? MRT_MODE_PER_WARP : MRT_MODE_PER_LANE);
     s->last_acc = acc;
     return MRT_OK;
@@ -644,7 +652,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     if (!s->rendered) { set_error("mrt_gpu_stats: nothing rendered yet"); return MRT_E_STATE; }
     int rc = mrt_gpu_wait(s);
     if (rc) return rc;
-    unsigned long long c[4];
+    unsigned long long c[8];
     CUDA_TRY(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->rays = c[0];
@@ -656,6 +664,8 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     out->block = s->last_block;
     out->smem_bytes = s->last_smem;
     out->mode = s->last_mode;
+    out->coop_trees = s->last_coop ? 1u : 0u;
+    out->coop_node_steps = c[4]; out->coop_node_items = c[5]; out->coop_leaf_steps = c[6]; out->coop_leaf_items = c[7];
     return MRT_OK;
 }
 

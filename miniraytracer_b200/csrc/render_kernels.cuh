@@ -14,6 +14,7 @@
 // Every accumulator element has exactly one writer: no float atomics, results are reproducible run to run.
 #pragma once
 #include "gpu_internal.h"
+#include "coop_tree.cuh"
 
 namespace mrt {
 
@@ -33,7 +34,7 @@ struct RenderArgs {
     uint32_t n_tasks, pixels_per_task;
     float4 *acc;
     unsigned int *ticket;             // global task counter
-    unsigned long long *counters;     // [0] rays [1] paths [2] nonfinite
+    unsigned long long *counters;     // [0] rays [1] warp iterations [2] nonfinite [4..7] cooperative traversal: node steps, node items, leaf steps, leaf items
     const uint32_t *order;            // work order: item i of the queue is pixel order[i] (Morton tiles), or NULL = row-major
     const volatile int *cancel;       // device flag, written by mrt_gpu_cancel through a side stream
     // binned mode (render_pixel_binned): per-warp path pool in global memory (L2 resident) and the ray classifier
@@ -60,6 +61,33 @@ __device__ __forceinline__ bool path_step(const RenderArgs &a, Path &p, Rng &rng
     path_advance(FEAT, a.sc, p);   // normalise the pending direction, apply the deferred diffuse weight
     bool hit = intersect(FEAT, a.sc, p.ray, 0.001f, FLT_MAX, rec, rng, st, nullptr);
     return path_shade(FEAT, a.sc, p, hit, rec, a.max_bounces, rng);
+}
+
+// The same with the warp-cooperative tree traversal (coop_tree.cuh); called by ALL lanes of the warp, active or not.
+// The per-lane machine runs up to the root of a BVH tree and suspends; the warp then traverses the trees of all suspended
+// lanes together; the lanes resume with the tree's outcome (a scene may hold several trees: one round per tree).
+template <uint32_t FEAT>
+__device__ __forceinline__ bool path_step_coop(const RenderArgs &a, Path &p, Rng &rng, Stack &st, bool active, CoopArea &ca, CoopStats &cs) {
+    Hit rec;
+    Isect s;
+    s.ret = false; s.cur = 0; s.tmin = 0; s.tmax = 0;
+    bool done = true;
+    if (active) {
+        path_advance(FEAT, a.sc, p);
+        isect_begin(s, a.sc, 0.001f, FLT_MAX, st);
+        done = isect_run<true>(FEAT, a.sc, p.ray, s, rec, rng, st, false, nullptr);
+    }
+    while (__any_sync(0xFFFFFFFFu, !done)) {
+        const bool job = !done;
+        const bool h = coop_traverse(FEAT, a.sc, ca, job, s.cur, p.ray, s.tmin, s.tmax, rec, cs);
+        if (job) {
+            s.ret = h;
+            if (h) s.tmax = rec.t;
+            done = isect_run<true>(FEAT, a.sc, p.ray, s, rec, rng, st, true, nullptr);
+        }
+    }
+    if (!active) return false;
+    return path_shade(FEAT, a.sc, p, s.ret, rec, a.max_bounces, rng);
 }
 
 // ------------------------------------------------------------------ mode W
@@ -294,7 +322,7 @@ __device__ __forceinline__ uint32_t ray_class(const RenderArgs &a, const Path &p
     return c;
 }
 
-template <uint32_t FEAT, int MINB>
+template <uint32_t FEAT, int MINB, bool COOP>
 __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const RenderArgs a) {
     extern __shared__ uint32_t smem_stack[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -305,6 +333,9 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     const uint32_t K = a.pixels_per_task, NB = a.n_bins;
     uint8_t *binq = reinterpret_cast<uint8_t *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * (NB + 1u) * kPoolCap;
     uint8_t *freeq = binq + (size_t) NB * kPoolCap;
+    CoopArea ca;
+    CoopStats cstats = {0, 0, 0, 0};
+    if (COOP) ca.bind(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u + (size_t) kWarpsPerBlock * (NB + 1u) * (kPoolCap / 4u) + (size_t) warp * kCoopWords);
     uint32_t *pool = a.pool + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) (kPoolCap * kStateWords);
     // finished samples go to a per-warp staging array indexed by item (global memory, written once, read once) and
     // are summed per pixel at the end of the chunk in ITEM order -- so the result does not depend on which lane ran
@@ -381,14 +412,13 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             }
             iters++;
             bool cont = false;
-            if (active) {
-                rays++;
-                cont = path_step<FEAT>(a, p, rng, st);
-                if (!cont) {
-                    const bool fin = path_sample_finite(p);
-                    __stcs(stage + k, fin ? make_float4(p.L.x, p.L.y, p.L.z, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f));
-                    if (!fin) nonfinite++;
-                }
+            if (active) rays++;
+            if constexpr (COOP) cont = path_step_coop<FEAT>(a, p, rng, st, active, ca, cstats);
+            else if (active) cont = path_step<FEAT>(a, p, rng, st);
+            if (active && !cont) {
+                const bool fin = path_sample_finite(p);
+                __stcs(stage + k, fin ? make_float4(p.L.x, p.L.y, p.L.z, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f));
+                if (!fin) nonfinite++;
             }
             // slots: finished paths return theirs, new survivors take one (never both in one iteration)
             const uint32_t m_free = __ballot_sync(0xFFFFFFFFu, active && !cont && slot != 0xFFu);
@@ -453,14 +483,22 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         atomicAdd(&a.counters[0], rays);
         atomicAdd(&a.counters[1], iters);
         atomicAdd(&a.counters[2], nonfinite);
+        if (COOP) {
+            atomicAdd(&a.counters[4], cstats.node_steps); atomicAdd(&a.counters[5], cstats.node_items);
+            atomicAdd(&a.counters[6], cstats.leaf_steps); atomicAdd(&a.counters[7], cstats.leaf_items);
+        }
     }
 }
 
 // kernel entry for a feature mask (defined once per render_variant_*.cu); kind: 0 = pixel per lane,
-// 1 = pixel per warp, 2 = pixel per warp with binned path pool
+// 1 = pixel per warp, 2 = pixel per warp with binned path pool, 3 = binned + warp-cooperative tree traversal (only
+// instantiated for masks with MRT_FEAT_TREES)
 template <uint32_t FEAT, int MINB>
 inline const void *variant_kernel_minb(int kind) {
-    if (kind == 2) return (const void *) render_pixel_binned<FEAT, MINB>;
+    if constexpr ((FEAT & MRT_FEAT_TREES) != 0) {
+        if (kind == 3) return (const void *) render_pixel_binned<FEAT, MINB, true>;
+    }
+    if (kind >= 2) return (const void *) render_pixel_binned<FEAT, MINB, false>;
     return kind ? (const void *) render_pixel_per_warp<FEAT, MINB> : (const void *) render_pixel_per_lane<FEAT, MINB>;
 }
 template <uint32_t FEAT>

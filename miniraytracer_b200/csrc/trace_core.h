@@ -418,20 +418,36 @@ MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float 
 //    (tmin, tmax) and only needs the two distances -> `probe` mode, in which
 //    hits update tmax only and the main record is untouched.  A volume's
 //    boundary must not contain another volume (checked by the flattener).
-MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
-                      Counters *cnt) {
-    float tmin = tmin0, tmax = tmax0;
-    float main_tmax = tmax0;
-    bool probe_v = false;
+// State of one scene.hit() call, kept by the caller so that the traversal can be suspended (COOP, see below).
+struct Isect {
+    float tmin0, tmin, tmax, main_tmax, vol_t1;
+    uint32_t cur, sp0;
+    bool ret, probe_v;
+};
+MRT_HD void isect_begin(Isect &s, const SceneView &sc, float tmin0, float tmax0, const Stack &st) {
+    s.tmin0 = tmin0; s.tmin = tmin0; s.tmax = tmax0; s.main_tmax = tmax0; s.vol_t1 = 0.0f;
+    s.cur = sc.root; s.sp0 = st.sp; s.ret = false; s.probe_v = false;
+}
+// Runs the traversal.  Returns true when it is finished (s.ret = hit, rec = record).
+// COOP = true (warp-cooperative tree traversal, coop_tree.cuh): the per-lane machine does not enter BVH trees.  When it
+// stands at the root of a tree whose own box the ray hits it returns FALSE with s.cur = the tree's root child; the
+// caller traverses the tree, stores the outcome in s.ret / rec (and s.tmax = rec.t on a hit) and calls again with
+// resume = true, which continues with the frame on top of the stack exactly as if the visit had returned.
+template <bool COOP>
+MRT_HD bool isect_run(const uint32_t feat, const SceneView &sc, Ray &ray, Isect &s, Hit &rec, Rng &rng, Stack &st, bool resume, Counters *cnt) {
+    const float tmin0 = s.tmin0;
+    float tmin = s.tmin, tmax = s.tmax;
+    float main_tmax = s.main_tmax;
+    bool probe_v = s.probe_v;
 #define probe (MRT_HAS(feat, MRT_FEAT_VOLUMES) && probe_v)
-    float vol_t1 = 0.0f;
-    uint32_t cur = sc.root;
-    bool ret = false;
-    const uint32_t sp0 = st.sp;
-
+    float vol_t1 = s.vol_t1;
+    uint32_t cur = s.cur;
+    bool ret = s.ret;
+    const uint32_t sp0 = s.sp0;
     for (;;) {
         // ------------------------------------------------------------ visit
-        bool descend = true;
+        bool descend = !resume;
+        resume = false;
         while (descend) {
             descend = false;
             const uint32_t type = MRT_REF_TYPE(cur), idx = MRT_REF_INDEX(cur);
@@ -452,10 +468,14 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
                 ret = false;
                 if (!aabb_hit(b0, b1, ray, tmin, tmax)) break;
                 cur = f2u(b0.w);
+                if (COOP) {   // suspend: the warp traverses the tree together
+                    s.tmin = tmin; s.tmax = tmax; s.main_tmax = main_tmax; s.probe_v = probe_v; s.vol_t1 = vol_t1; s.cur = cur; s.ret = false;
+                    return false;
+                }
                 descend = true;
                 break;
             }
-            case MRT_T_NODE2: if (!MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {
+            case MRT_T_NODE2: if (COOP || !MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {
                 // Inner node carrying both children's boxes.  Visit the closer child (node_order & dirMask,
                 // scene_object.h:224-231) if its box is hit; the farther one only if the closer reports no hit
                 // (IF_MISS frame).  tmin/tmax are constant inside a tree, so the child box tests made here are
@@ -489,7 +509,7 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
                 }
                 break;
             }
-            case MRT_T_TRILEAF: if (!MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
+            case MRT_T_TRILEAF: if (COOP || !MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
                 const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
                 ret = false;
                 for (uint32_t i = 0; i < count; i++) {
@@ -563,10 +583,10 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
 
         // ----------------------------------------------------------- return
         for (;;) {
-            if (st.sp == sp0) return ret && !probe;
+            if (st.sp == sp0) { s.ret = ret && !probe; return true; }
             uint32_t e = st.pop();
             uint32_t tag = e >> 29;
-            if (MRT_HAS(feat, MRT_FEAT_TREES) && tag == MRT_F_IF_MISS) {
+            if (!COOP && MRT_HAS(feat, MRT_FEAT_TREES) && tag == MRT_F_IF_MISS) {
                 if (ret) continue;
                 cur = e & 0x0FFFFFFFu;
                 break;
@@ -660,6 +680,14 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
     }
 }
 #undef probe
+
+MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float tmin0, float tmax0, Hit &rec, Rng &rng, Stack &st,
+                      Counters *cnt) {
+    Isect s;
+    isect_begin(s, sc, tmin0, tmax0, st);
+    isect_run<false>(feat, sc, ray, s, rec, rng, st, false, cnt);
+    return s.ret;
+}
 
 // ------------------------------------------------------------------- textures
 // texture.cpp:68-165

@@ -29,10 +29,12 @@ struct FileHeader {
 
 static RenderArgs g_args;
 static char g_mode = 'B';
+static bool g_coop = false;
 static void entry(void *) {
     if (g_mode == 'W') render_pixel_per_warp<MRT_FEAT_ALL, 6>(g_args);
     else if (g_mode == 'P') render_pixel_per_lane<MRT_FEAT_ALL, 6>(g_args);
-    else render_pixel_binned<MRT_FEAT_ALL, 6>(g_args);
+    else if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true>(g_args);
+    else render_pixel_binned<MRT_FEAT_ALL, 6, false>(g_args);
 }
 
 int main(int argc, char **argv) {
@@ -42,6 +44,7 @@ int main(int argc, char **argv) {
     uint64_t seed = strtoull(argval(argc, argv, "-seed", "11350390909718046443"), 0, 0);
     uint32_t chunk = strtoul(argval(argc, argv, "-chunk", "0"), 0, 0), bins = strtoul(argval(argc, argv, "-bins", "2"), 0, 0);
     g_mode = argval(argc, argv, "-mode", "B")[0];
+    g_coop = atoi(argval(argc, argv, "-coop", "0")) != 0;   // warp-cooperative tree traversal (coop_tree.cuh)
     std::string assets = argval(argc, argv, "-assets", "assets");
     const char *out = argval(argc, argv, "-out", nullptr);
 
@@ -72,6 +75,10 @@ int main(int argc, char **argv) {
     a.width = W; a.height = H; a.sqrt_n = sq; a.s_begin = s0; a.s_end = s1; a.max_bounces = depth; a.seed = seed;
     a.accumulate = 0;
     a.stack_words = d.stack_words ? d.stack_words : 64;
+    if (g_coop) {
+        if (!d.stack_words_coop) { fprintf(stderr, "the scene's trees do not qualify for the cooperative traversal\n"); return 1; }
+        a.stack_words = d.stack_words_coop;
+    }
     uint32_t K = chunk ? chunk : (256u / ns ? 256u / ns : 1u);   // small chunks: several tasks per warp even on a tiny frame
     if ((uint64_t) K * ns > kMaxStageItems) K = kMaxStageItems / ns;
     if (K < 1) K = 1;
@@ -91,7 +98,7 @@ int main(int argc, char **argv) {
     std::vector<float4> acc(n_pixels, make_float4(0, 0, 0, 0));
     a.acc = acc.data();
     unsigned int ticket = 0;
-    unsigned long long counters[4] = {0, 0, 0, 0};
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cancel = 0;
     a.ticket = &ticket; a.counters = counters; a.cancel = &cancel; a.order = nullptr;
     const uint32_t warps = kWarpsPerBlock;
@@ -100,7 +107,7 @@ int main(int argc, char **argv) {
     std::vector<float4> stage((size_t) warps * a.stage_items, make_float4(0, 0, 0, 0));
     a.pool = pool.data(); a.stage = stage.data();
     const size_t smem_words = (size_t) warps * a.stack_words * 32u + ((size_t) warps * (a.n_bins + 1u) * kPoolCap + 3u) / 4u +
-                              (g_mode == 'W' ? (size_t) warps * K * 32u * 4u : 0u);
+                              (g_mode == 'W' ? (size_t) warps * K * 32u * 4u : 0u) + (g_coop ? (size_t) warps * kCoopWords : 0u);
     if (smem_words > sizeof(smem_stack) / 4) { fprintf(stderr, "shared memory emulation too small\n"); return 1; }
 
     emul::run_block(entry, nullptr, kBlock, 0);
@@ -117,7 +124,8 @@ int main(int argc, char **argv) {
         fwrite(acc.data(), sizeof(float4), acc.size(), f);
         fclose(f);
     }
-    printf("{\"rays\": %llu, \"iterations\": %llu, \"nonfinite\": %llu, \"collectives\": %llu, \"tasks\": %u, \"bins\": %u}\n", counters[0], counters[1], counters[2],
-           emul::g_collectives, a.n_tasks, a.n_bins);
+    printf("{\"rays\": %llu, \"iterations\": %llu, \"nonfinite\": %llu, \"collectives\": %llu, \"tasks\": %u, \"bins\": %u, "
+           "\"coop_node_steps\": %llu, \"coop_node_items\": %llu, \"coop_leaf_steps\": %llu, \"coop_leaf_items\": %llu}\n", counters[0], counters[1], counters[2],
+           emul::g_collectives, a.n_tasks, a.n_bins, counters[4], counters[5], counters[6], counters[7]);
     return 0;
 }

@@ -4,6 +4,7 @@
 // collective (__shfl_sync, __ballot_sync, __syncwarp), which is exactly the lockstep the kernels rely on at those
 // points.  One block at a time (the dynamic shared memory is one global array).  Nothing here ships.
 #pragma once
+#define MRT_EMUL_WARP 1
 #include <cuda_runtime.h>   // vector types only; the CUDA function qualifiers are neutralised below
 #include <ucontext.h>
 
@@ -133,6 +134,7 @@ inline void __threadfence_block() {}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }

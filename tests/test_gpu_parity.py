@@ -306,3 +306,26 @@ def test_crop_window_equals_full_frame():
     assert st["rays"] == meta["rays"]
     with pytest.raises(api.MrtError):
         _gpu_render(7, w, h, spp, crop=(10, 10, 10, 20))
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [(0, 160, 160, 16), (1, 96, 96, 36), (7, 160, 90, 36), (8, 160, 90, 36)])
+def test_cooperative_tree_traversal_is_bit_identical(scene, w, h, spp):
+    """Mode B traverses BVH trees warp-cooperatively by default (coop_tree.cuh: shared work stack, the hit of the leaf with
+    the lowest depth-first rank wins).  Every box / primitive test is the per-lane traversal's, so the accumulator is
+    bit-identical to MrtTuning.coop_trees = 1 (per-lane depth-first traversal) and the trace() count is equal."""
+    lane, st1 = _gpu_render(scene, w, h, spp, tuning=dict(coop_trees=1))
+    coop, st2 = _gpu_render(scene, w, h, spp, tuning=dict(coop_trees=2))
+    dflt, st0 = _gpu_render(scene, w, h, spp)
+    assert (st1["coop_trees"], st2["coop_trees"], st0["coop_trees"]) == (0, 1, 1)
+    assert st2["coop_node_steps"] > 0 and st2["coop_leaf_steps"] > 0 and st1["coop_node_steps"] == 0
+    assert st1["rays"] == st2["rays"] == st0["rays"]
+    np.testing.assert_array_equal(coop, lane)
+    np.testing.assert_array_equal(dflt, lane)
+
+
+def test_cooperative_traversal_not_applicable():
+    """Scenes without BVH trees (Cornell box) cannot ask for the cooperative traversal; the default silently does not use it."""
+    _, st = _gpu_render(5, 64, 36, 16)
+    assert st["coop_trees"] == 0
+    with pytest.raises(api.MrtError):
+        _gpu_render(5, 64, 36, 16, tuning=dict(coop_trees=2))

@@ -74,3 +74,17 @@ def test_mode_b_crop_window_at_true_config_size(emul_kernel_bin, scene, w, h, sp
     ref, rmeta = oracle_util.ref_render(scene, w, h, spp, s0=s0, s1=s1, crop=crop)
     acc, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, s0=s0, s1=s1, crop=crop)
     _same(acc, ref, meta["rays"], rmeta["rays"])
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp", [(8, 16, 9, 16), (0, 16, 16, 9), (1, 12, 12, 9), (7, 20, 11, 16)])
+def test_cooperative_tree_traversal_matches_oracle_and_per_lane(emul_kernel_bin, scene, w, h, spp):
+    """Warp-cooperative BVH traversal (coop_tree.cuh) in the CPU SIMT emulation: same trace() count as the oracle, accumulator
+    bit-identical to the per-lane depth-first traversal (every box / primitive test is the same function on the same operands;
+    the leaf with the lowest depth-first rank wins)."""
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp)
+    coop, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, extra=["-coop", "1"])
+    lane, meta0 = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp)
+    assert meta["info"]["coop_node_steps"] > 0 and meta["info"]["coop_leaf_steps"] > 0 and meta0["info"]["coop_node_steps"] == 0
+    np.testing.assert_array_equal(coop, lane)
+    _same(coop, ref, meta["rays"], rmeta["rays"])

@@ -30,9 +30,12 @@ def measure(case, tuning, reps=2, depth=32):
             best = st
     r.close(); hs.close()
     res = {"case": case, "kernel_ms": best["kernel_ms"], "grays_per_s": best["rays"] / best["kernel_ms"] / 1e6,
-           "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"], "mode": best["mode"],
-           "alive_frac": best["rays"] / max(1, 32 * best["warp_iterations"]), "depth": depth}
-    res.update(tuning)
+           "mpaths_per_s": best["paths"] / best["kernel_ms"] / 1e3, "grid": best["grid"], "smem": best["smem_bytes"], "ran_mode": best["mode"], "ran_coop": best["coop_trees"],
+           "alive_frac": best["rays"] / max(1, 32 * best["warp_iterations"]), "depth": depth,
+           "coop_node_fill": best["coop_node_items"] / max(1, 32 * best["coop_node_steps"]),
+           "coop_leaf_fill": best["coop_leaf_items"] / max(1, 32 * best["coop_leaf_steps"]),
+           "coop_node_items_per_ray": best["coop_node_items"] / max(1, best["rays"])}
+    res["tuning"] = {k: v for k, v in tuning.items() if v}
     return res
 
 
