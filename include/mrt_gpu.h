@@ -106,7 +106,8 @@ typedef struct MrtTuning {
     uint32_t variant_all;  /* 1 = the unspecialised kernel (all scene features compiled in) */
     uint32_t z_order;      /* 1 = hand out pixels along a Z-curve instead of row-major */
     uint32_t coop_trees;   /* BVH trees: 0 = default, 1 = per-lane traversal, 2 = warp-cooperative traversal */
-    uint32_t reserved[9];
+    uint32_t coop_leaf_batch; /* cooperative traversal: leaves queued before a leaf step runs, 1..32 (0 = default) */
+    uint32_t reserved[8];
 } MrtTuning;
 #define MRT_MODE_AUTO 0u
 #define MRT_MODE_PER_LANE 1u /* a lane owns a pixel and adds its samples in the reference's order (main.cpp:154-166) */

@@ -27,7 +27,8 @@
 //   bvh[2*i+1]    = (root box.max.xyz, 0)
 //   node2[4*i+0]  = (left  box.min.xyz, bits(left ref  | (order & 15) << 28))
 //   node2[4*i+1]  = (left  box.max.xyz, bits(right ref | (order >> 4) << 28))
-//   node2[4*i+2]  = (right box.min.xyz, bits(flags))  flags bit0/bit1: left/right child has a box to test
+//   node2[4*i+2]  = (right box.min.xyz, bits(flags))  flags bit0/bit1: left/right child has a box to test; bits 2-3 / 4-5: kind of
+//                   the left / right child (0 inner node, 1 object_list, 2 triangle leaf) for the warp-cooperative traversal
 //   node2[4*i+3]  = (right box.max.xyz, 0)
 //                   child refs: NODE2 (inner), LIST (header copy with hasBox = 0: its box is the one stored
 //                   here), TRILEAF, or any other object (no box flag -> visited unconditionally)
@@ -102,7 +103,10 @@ enum MrtMatKind {
 #define MRT_FEAT_DIELECTRIC 32u
 #define MRT_FEAT_MOVING 64u    /* moving spheres */
 #define MRT_FEAT_LIGHT_SPHERE 128u /* the light list holds something other than xz_rects */
-#define MRT_FEAT_ALL 255u
+#define MRT_FEAT_SPHERES 256u     /* the scene has spheres */
+#define MRT_FEAT_TRIS 512u        /* triangle leaves (pod_bvh) */
+#define MRT_FEAT_LEAF_LISTS 1024u /* some tree leaf is an object_list (bvh_node leaves) */
+#define MRT_FEAT_ALL 2047u
 
 enum MrtTexKind { MRT_X_COLOR = 0, MRT_X_CHECKER = 1, MRT_X_PERLIN = 2, MRT_X_IMAGE = 3 };
 

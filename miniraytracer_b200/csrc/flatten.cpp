@@ -150,7 +150,10 @@ struct Flattener {
     void fill_node2(uint32_t i, const Aabb &lb, bool lhas, uint32_t l, const Aabb &rb, bool rhas, uint32_t r, uint8_t order) {
         o.node2[4 * i + 0] = f4(lb.min.x, lb.min.y, lb.min.z, ubits(l | ((uint32_t) (order & 15u) << 28)));
         o.node2[4 * i + 1] = f4(lb.max.x, lb.max.y, lb.max.z, ubits(r | ((uint32_t) (order >> 4) << 28)));
-        o.node2[4 * i + 2] = f4(rb.min.x, rb.min.y, rb.min.z, ubits((lhas ? 1u : 0u) | (rhas ? 2u : 0u)));
+        // flags: bit 0 / 1 = the left / right child has a box to test; bits 2-3 / 4-5 = kind of the left / right child for the
+        // warp-cooperative traversal (coop_tree.cuh: 0 inner node, 1 object_list leaf, 2 triangle leaf)
+        auto kind = [](uint32_t ref) { return MRT_REF_TYPE(ref) == MRT_T_NODE2 ? 0u : (MRT_REF_TYPE(ref) == MRT_T_TRILEAF ? 2u : 1u); };
+        o.node2[4 * i + 2] = f4(rb.min.x, rb.min.y, rb.min.z, ubits((lhas ? 1u : 0u) | (rhas ? 2u : 0u) | (kind(l) << 2) | (kind(r) << 4)));
         o.node2[4 * i + 3] = f4(rb.max.x, rb.max.y, rb.max.z, 0);
     }
     std::map<int, uint32_t> inner_memo;
@@ -435,6 +438,16 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &op
         }
         for (const Node &n : g.nodes) if (n.kind == NodeKind::Sphere && n.moving) f |= MRT_FEAT_MOVING;
         for (uint32_t l : o.lights) if (MRT_REF_TYPE(l) != MRT_T_RECT_XZ) f |= MRT_FEAT_LIGHT_SPHERE;
+        if (!o.sphere.empty()) f |= MRT_FEAT_SPHERES;
+        if (!o.trileaf.empty()) f |= MRT_FEAT_TRIS;
+        for (size_t i = 0; i < o.node2.size(); i += 4) {   // kinds of the two children, see fill_node2
+            const uint32_t fl = ubits_of(o.node2[i + 2].w);
+            if (((fl >> 2) & 3u) == 1u || ((fl >> 4) & 3u) == 1u) f |= MRT_FEAT_LEAF_LISTS;
+        }
+        for (size_t i = 0; i < o.bvh.size(); i += 2) {
+            const uint32_t t = MRT_REF_TYPE(ubits_of(o.bvh[i].w));
+            if (t != MRT_T_NODE2 && t != MRT_T_TRILEAF) f |= MRT_FEAT_LEAF_LISTS;
+        }
         d.features = f;
     }
     const Camera &c = g.camera;

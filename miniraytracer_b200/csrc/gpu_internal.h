@@ -29,7 +29,7 @@ struct MrtScene {
     mrt::SceneView view;
     uint32_t stack_words = 0, stack_words_coop = 0;
     MrtTuning tuning = {};        // mrt_gpu_set_tuning; all zero = measured defaults
-    uint32_t has_trees = 0;
+    uint32_t has_trees = 0, n_node2 = 0;
     uint32_t features = 0;        // MRT_FEAT_* mask of the scene -> kernel variant (render_variants.h)
     cudaStream_t stream = nullptr;
     cudaStream_t poll_stream = nullptr;

@@ -340,6 +340,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     s->stack_words = d->stack_words ? d->stack_words : 64;
     s->stack_words_coop = d->stack_words_coop;   // 0: trees do not qualify for the warp-cooperative traversal
     s->has_trees = d->n_node2 ? 1u : 0u;
+    s->n_node2 = d->n_node2;
     s->features = d->features;
     find_classifier_boxes(d, s);
 
@@ -368,7 +369,7 @@ extern "C" int mrt_gpu_set_tuning(MrtScene *s, const MrtTuning *t) {
     MrtTuning z;
     memset(&z, 0, sizeof(z));
     if (t) z = *t;
-    if (z.mode > MRT_MODE_BINNED || z.bins > 3u || (z.min_blocks && (z.min_blocks < 5u || z.min_blocks > 8u)) || z.coop_trees > 2u) {
+    if (z.mode > MRT_MODE_BINNED || z.bins > 3u || (z.min_blocks && (z.min_blocks < 5u || z.min_blocks > 8u)) || z.coop_trees > 2u || z.coop_leaf_batch > 32u) {
         set_error("mrt_gpu_set_tuning: value out of range");
         return MRT_E_INVALID;
     }
@@ -491,7 +492,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     // BVH trees: warp-cooperative traversal (coop_tree.cuh) in mode B where the scene's trees qualify
     const bool coop_ok = binned && s->has_trees && s->stack_words_coop != 0u && (variant->mask & MRT_FEAT_TREES);
     if (tn.coop_trees == 2u && !coop_ok) { set_error("mrt_gpu_render_async: cooperative tree traversal needs mode B and qualifying trees"); return MRT_E_INVALID; }
-    const bool coop = coop_ok && tn.coop_trees != 1u;
+    // default: only where it pays -- big trees (triangle meshes); the small sphere / box trees of scenes 0, 1, 7 are faster per lane
+    // (profiles/r2_notes.md)
+    const bool coop = coop_ok && (tn.coop_trees == 2u || (tn.coop_trees == 0u && s->n_node2 >= 1024u));
     const void *kernel = variant->get(coop ? 3 : (binned ? 2 : (mode_w ? 1 : 0)), minb);
     const uint32_t stack_words = coop ? s->stack_words_coop : s->stack_words;
     uint32_t n_bins = 1;
@@ -507,6 +510,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         n_bins = 1u << (a.n_cls_boxes + a.cls_pending);
     }
     a.n_bins = n_bins;
+    a.coop_leaf_batch = tn.coop_leaf_batch ? tn.coop_leaf_batch : 32u;
     const uint32_t threads = kBlock;
     const uint32_t warps_per_block = threads / 32u;
     // choose the task size so that every resident warp gets several tasks (load balance) while the idle

@@ -43,6 +43,7 @@ struct RenderArgs {
     uint32_t stage_items;             // pixels_per_task * samples of this launch (<= kMaxStageItems)
     uint32_t n_bins;                  // 1 << (n_cls_boxes + cls_pending)
     uint32_t n_cls_boxes, cls_pending;
+    uint32_t coop_leaf_batch;         // cooperative tree traversal: a leaf step runs once this many leaves are queued (1..32)
     float cls_box[kMaxClsBoxes][6];   // world-space boxes (min xyz, max xyz) of the root list's composite children
 };
 
@@ -71,19 +72,20 @@ __device__ __forceinline__ bool path_step_coop(const RenderArgs &a, Path &p, Rng
     Hit rec;
     Isect s;
     s.ret = false; s.cur = 0; s.tmin = 0; s.tmax = 0;
-    bool done = true;
     if (active) {
         path_advance(FEAT, a.sc, p);
         isect_begin(s, a.sc, 0.001f, FLT_MAX, st);
-        done = isect_run<true>(FEAT, a.sc, p.ray, s, rec, rng, st, false, nullptr);
     }
-    while (__any_sync(0xFFFFFFFFu, !done)) {
+    bool done = !active, resume = false;
+    for (;;) {   // one call site of the per-lane machine (instruction-cache footprint)
+        if (!done) done = isect_run<true>(FEAT, a.sc, p.ray, s, rec, rng, st, resume, nullptr);
+        if (!__any_sync(0xFFFFFFFFu, !done)) break;
         const bool job = !done;
-        const bool h = coop_traverse(FEAT, a.sc, ca, job, s.cur, p.ray, s.tmin, s.tmax, rec, cs);
+        const bool h = coop_traverse(FEAT, a.sc, ca, job, s.cur, p.ray, s.tmin, s.tmax, rec, cs, a.coop_leaf_batch);
         if (job) {
             s.ret = h;
             if (h) s.tmax = rec.t;
-            done = isect_run<true>(FEAT, a.sc, p.ray, s, rec, rng, st, true, nullptr);
+            resume = true;
         }
     }
     if (!active) return false;
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     uint8_t *freeq = binq + (size_t) NB * kPoolCap;
     CoopArea ca;
     CoopStats cstats = {0, 0, 0, 0};
+    unsigned long long cs_node_steps = 0, cs_node_items = 0, cs_leaf_steps = 0, cs_leaf_items = 0;
     if (COOP) ca.bind(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u + (size_t) kWarpsPerBlock * (NB + 1u) * (kPoolCap / 4u) + (size_t) warp * kCoopWords);
     uint32_t *pool = a.pool + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) (kPoolCap * kStateWords);
     // finished samples go to a per-warp staging array indexed by item (global memory, written once, read once) and
@@ -445,6 +448,10 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             }
             __syncwarp();
         }
+        if (COOP) {   // 32-bit per-chunk counters -> 64-bit totals
+            cs_node_steps += cstats.node_steps; cs_node_items += cstats.node_items; cs_leaf_steps += cstats.leaf_steps; cs_leaf_items += cstats.leaf_items;
+            cstats.node_steps = cstats.node_items = cstats.leaf_steps = cstats.leaf_items = 0u;
+        }
         __syncwarp();
         __threadfence_block();   // this warp's staged samples (written by other lanes) are visible to every lane
 #pragma unroll 1
@@ -484,8 +491,8 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         atomicAdd(&a.counters[1], iters);
         atomicAdd(&a.counters[2], nonfinite);
         if (COOP) {
-            atomicAdd(&a.counters[4], cstats.node_steps); atomicAdd(&a.counters[5], cstats.node_items);
-            atomicAdd(&a.counters[6], cstats.leaf_steps); atomicAdd(&a.counters[7], cstats.leaf_items);
+            atomicAdd(&a.counters[4], cs_node_steps); atomicAdd(&a.counters[5], cs_node_items);
+            atomicAdd(&a.counters[6], cs_leaf_steps); atomicAdd(&a.counters[7], cs_leaf_items);
         }
     }
 }

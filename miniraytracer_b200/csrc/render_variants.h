@@ -9,16 +9,18 @@
 namespace mrt {
 
 // exact masks of the two Cornell configurations (no metal; C3 has no dielectric either)
-#define MRT_VARIANT_CORNELL (MRT_FEAT_XFORM | MRT_FEAT_DIELECTRIC)
+#define MRT_VARIANT_CORNELL (MRT_FEAT_XFORM | MRT_FEAT_DIELECTRIC | MRT_FEAT_SPHERES)
 #define MRT_VARIANT_CORNELL_VOL (MRT_FEAT_XFORM | MRT_FEAT_VOLUMES)
 // Cornell-style scenes: lists, rects, spheres, transforms; lambertian / metal / dielectric / light; colour textures
-#define MRT_VARIANT_LISTS (MRT_FEAT_XFORM | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
+#define MRT_VARIANT_LISTS (MRT_FEAT_XFORM | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC | MRT_FEAT_SPHERES)
 // ... plus constant-density volumes
 #define MRT_VARIANT_LISTS_VOL (MRT_VARIANT_LISTS | MRT_FEAT_VOLUMES)
-// tree scenes without transforms, volumes and procedural / image textures (triangle meshes in a Cornell box)
-#define MRT_VARIANT_TREES (MRT_FEAT_TREES | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
-// sphere BVH with procedural textures and motion blur ("In One Weekend")
-#define MRT_VARIANT_TREES_TEX (MRT_VARIANT_TREES | MRT_FEAT_TEX | MRT_FEAT_MOVING)
+// triangle meshes in a Cornell box: no spheres, no transforms, volumes, procedural / image textures
+#define MRT_VARIANT_TREES (MRT_FEAT_TREES | MRT_FEAT_TRIS | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC)
+// sphere BVH (object_list leaves) with procedural textures and motion blur ("In One Weekend").  MRT_FEAT_TRIS stays in although
+// these scenes have no triangles: without the triangle-leaf case nvcc 12.9 lays the per-lane traversal loop out differently
+// and the kernel is 57 % SLOWER on scene 0 (measured, profiles/r2_notes.md) -- a code-generation accident, kept on the good side
+#define MRT_VARIANT_TREES_TEX (MRT_FEAT_TREES | MRT_FEAT_TRIS | MRT_FEAT_LEAF_LISTS | MRT_FEAT_SPHERES | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC | MRT_FEAT_TEX | MRT_FEAT_MOVING)
 
 const void *variant_cornell(int kind, int minb);
 const void *variant_cornell_vol(int kind, int minb);

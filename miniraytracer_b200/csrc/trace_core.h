@@ -509,7 +509,7 @@ MRT_HD bool isect_run(const uint32_t feat, const SceneView &sc, Ray &ray, Isect 
                 }
                 break;
             }
-            case MRT_T_TRILEAF: if (COOP || !MRT_HAS(feat, MRT_FEAT_TREES)) { ret = false; break; } {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
+            case MRT_T_TRILEAF: if (COOP || !MRT_HAS(feat, MRT_FEAT_TREES) || !MRT_HAS(feat, MRT_FEAT_TRIS)) { ret = false; break; } {   // pod_bvh leaf: closest hit among its triangles (triangle.h:179-187)
                 const uint32_t first = ldu(sc.trileaf, 2 * idx), count = ldu(sc.trileaf, 2 * idx + 1);
                 ret = false;
                 for (uint32_t i = 0; i < count; i++) {
@@ -600,7 +600,7 @@ MRT_HD bool isect_run(const uint32_t feat, const SceneView &sc, Ray &ray, Isect 
                     uint32_t ctype = MRT_REF_TYPE(c);
                     if (ctype == MRT_T_END) break;
                     ci++;
-                    if (ctype == MRT_T_SPHERE) {
+                    if (MRT_HAS(feat, MRT_FEAT_SPHERES) && ctype == MRT_T_SPHERE) {
                         if (cnt) cnt->sphere++;
                         if (hit_sphere(feat, sc, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
                     } else if (ctype <= MRT_T_RECT_YZ) {
@@ -787,7 +787,7 @@ MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin
                 float cosine = fabsf(dot(dir, v3(0, q1.y, 0)));
                 pv = fdiv(dist_sq, (cosine * area));
             }
-        } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && type == MRT_T_SPHERE) {
+        } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && MRT_HAS(feat, MRT_FEAT_SPHERES) && type == MRT_T_SPHERE) {
             if (hit_sphere(feat, sc, idx, r, 0.001f, FLT_MAX, false, rec)) {
                 MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
                 V3 cen = sphere_center(s0, s1, sc.sphere, idx, time);
@@ -824,7 +824,7 @@ MRT_FN V3 light_pdf_generate(const uint32_t feat, const SceneView &sc, V3 origin
         float rx = randf(rng), rz = randf(rng);
         V3 rnd = v3(q0.x + rx * (q0.y - q0.x), q1.x, q0.z + rz * (q0.w - q0.z));
         return rnd - origin;
-    } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && type == MRT_T_SPHERE) {
+    } else if (MRT_HAS(feat, MRT_FEAT_LIGHT_SPHERE) && MRT_HAS(feat, MRT_FEAT_SPHERES) && type == MRT_T_SPHERE) {
         MrtF4 s0 = ld4(sc.sphere, 3 * idx), s1 = ld4(sc.sphere, 3 * idx + 1);
         V3 dir = sphere_center(s0, s1, sc.sphere, idx, time) - origin;
         float dist_sq = sdot(dir);

@@ -95,6 +95,7 @@ int main(int argc, char **argv) {
         if (bins >= 3) a.cls_pending = 1;
     }
     a.n_bins = 1u << (a.n_cls_boxes + a.cls_pending);
+    a.coop_leaf_batch = strtoul(argval(argc, argv, "-leafbatch", "16"), 0, 0);
     std::vector<float4> acc(n_pixels, make_float4(0, 0, 0, 0));
     a.acc = acc.data();
     unsigned int ticket = 0;

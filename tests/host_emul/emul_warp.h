@@ -118,6 +118,11 @@ inline uint32_t smem_stack[64 * 1024];   // the kernels' `extern __shared__ uint
 template <typename T> inline T emul_bits_to(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
 template <typename T> inline uint64_t emul_bits_of(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> inline T __shfl_sync(unsigned, T v, unsigned src) { return emul_bits_to<T>(emul::exchange(emul_bits_of(v))[src & 31u]); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+    const uint32_t lane = emul::g_lane->tid & 31u;
+    const uint64_t *b = emul::exchange(emul_bits_of(v));
+    return lane >= delta ? emul_bits_to<T>(b[lane - delta]) : v;
+}
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int mask) {
     const uint32_t lane = emul::g_lane->tid & 31u;
     return emul_bits_to<T>(emul::exchange(emul_bits_of(v))[(lane ^ (uint32_t) mask) & 31u]);
@@ -135,6 +140,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }

@@ -310,13 +310,16 @@ def test_crop_window_equals_full_frame():
 
 @pytest.mark.parametrize("scene,w,h,spp", [(0, 160, 160, 16), (1, 96, 96, 36), (7, 160, 90, 36), (8, 160, 90, 36)])
 def test_cooperative_tree_traversal_is_bit_identical(scene, w, h, spp):
-    """Mode B traverses BVH trees warp-cooperatively by default (coop_tree.cuh: shared work stack, the hit of the leaf with
-    the lowest depth-first rank wins).  Every box / primitive test is the per-lane traversal's, so the accumulator is
-    bit-identical to MrtTuning.coop_trees = 1 (per-lane depth-first traversal) and the trace() count is equal."""
+    """Mode B can traverse BVH trees warp-cooperatively (coop_tree.cuh: shared work stack, the hit of the leaf with the
+    lowest depth-first rank wins; the default for big trees = the triangle meshes of scene 8).  Every box / primitive test
+    is the per-lane traversal's, so the accumulator is bit-identical to MrtTuning.coop_trees = 1 (per-lane depth-first
+    traversal) and the trace() count is equal; the leaf batch size does not matter either."""
     lane, st1 = _gpu_render(scene, w, h, spp, tuning=dict(coop_trees=1))
     coop, st2 = _gpu_render(scene, w, h, spp, tuning=dict(coop_trees=2))
     dflt, st0 = _gpu_render(scene, w, h, spp)
-    assert (st1["coop_trees"], st2["coop_trees"], st0["coop_trees"]) == (0, 1, 1)
+    assert (st1["coop_trees"], st2["coop_trees"], st0["coop_trees"]) == (0, 1, 1 if scene == 8 else 0)
+    odd, st3 = _gpu_render(scene, w, h, spp, tuning=dict(coop_trees=2, coop_leaf_batch=5))
+    np.testing.assert_array_equal(odd, lane)
     assert st2["coop_node_steps"] > 0 and st2["coop_leaf_steps"] > 0 and st1["coop_node_steps"] == 0
     assert st1["rays"] == st2["rays"] == st0["rays"]
     np.testing.assert_array_equal(coop, lane)
