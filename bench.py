@@ -1,18 +1,20 @@
 #!/usr/bin/env python3
-"""Headline benchmark: Mpath-samples/s (+ Grays/s) of the path-tracing bounce loop on BASELINE.json's
-configs[1] -- Cornell box (scene 5), 1920x1080, 1024 spp, 32 bounces -- on N B200s of one node.
+"""Benchmark of the path-tracing bounce loop: Mpath-samples/s (+ Grays/s) on N B200s of one node.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA renderer
   python bench.py --impl reference [...]                         the reference's own CPU renderer (oracle/_ref)
   torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU
 
-A step = one full render of the workload.  With N GPUs the samples per pixel are split into N slices of
-disjoint PCG streams (each rank renders the whole frame for its slice), the float4 accumulators are
-sum-reduced with one NCCL all-reduce and finalised (mean over finite samples + luminance clamp) -- total work
-is fixed, so scaling is "strong".  One JSON line is printed by rank 0.
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] -- Cornell box (scene 5), 1920x1080, 1024 spp, 32 bounces.
+`per_config` carries the other four BASELINE configs (C1, C3, C4, C5) on the same GPUs: device-timed Mpaths/s, Grays/s, kernel
+time, roofline fraction, live-lane share, end-to-end figure and the steps / sizes actually run (C5 = 4K x 4096 spp is run in full
+on 8 GPUs and with a stated, reduced sample count otherwise).
+
+A step = one full render of the workload.  With N GPUs the samples per pixel are split into N slices of disjoint PCG streams
+(each rank renders the whole frame for its slice), the float4 accumulators are sum-reduced with one NCCL all-reduce and finalised
+(mean over finite samples + luminance clamp) -- total work is fixed, so scaling is "strong".  One JSON line is printed by rank 0.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -24,12 +26,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (scene, width, height, spp, depth, algorithmic flop per ray -- SURVEY.md section 8d)
-    "C1": (0, 500, 500, 16, 32, 832.0),
-    "C2": (5, 1920, 1080, 1024, 32, 294.0),
-    "C3": (6, 1920, 1080, 1024, 32, 336.0),
-    "C4": (7, 1920, 1080, 4096, 32, 813.0),
-    "C5": (8, 3840, 2160, 4096, 32, 1258.0),
+    # name: (scene, width, height, spp, depth)
+    "C1": (0, 500, 500, 16, 32),
+    "C2": (5, 1920, 1080, 1024, 32),
+    "C3": (6, 1920, 1080, 1024, 32),
+    "C4": (7, 1920, 1080, 4096, 32),
+    "C5": (8, 3840, 2160, 4096, 32),
 }
 WORKLOAD_DESC = {
     "C1": "'In One Weekend' random spheres 500x500, 16 spp, 32 bounces",
@@ -39,11 +41,12 @@ WORKLOAD_DESC = {
     "C5": "triangle meshes (bunny + teapot) 3840x2160, 4096 spp, 32 bounces",
 }
 FP32_LANES_PER_SM = 128
-# From the ncu --set full capture of this bench's render kernel (profiles/r1k_ncu_full_bench_kernel.csv, C2, mode B):
-# warp-level instructions executed per ray and DRAM bytes per launch.  Used only for the derived
-# "issue_slots_frac_est" / "traffic" fields; the primary roofline numbers are measured live.
-NCU_WARP_INST_PER_RAY = {"C2": 247536525255 / 4561710601}
-NCU_DRAM_BYTES_PER_LAUNCH = {"C2": 21506226000 + 33954349000}
+
+
+def alg_flop_per_ray():
+    """Algorithmic flop per ray of each config, derived from operation counters by tools/alg_flops.py."""
+    d = json.load(open(os.path.join(ROOT, "tools", "alg_flops.json")))
+    return {k: float(v["flop_per_ray"]) for k, v in d["configs"].items()}
 
 
 def measured_peaks():
@@ -51,6 +54,11 @@ def measured_peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         return {}
+
+
+def config_dict(name, scene, W, H, spp, depth):
+    """The SAME dict in both arms (the driver compares them)."""
+    return {"workload": name + ": " + WORKLOAD_DESC[name], "scene": scene, "width": W, "height": H, "spp": spp, "max_bounces": depth}
 
 
 class ClockSampler(threading.Thread):
@@ -94,42 +102,90 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+_REF_BIN = None
+
+
+def reference_binary():
+    """The reference built with ITS OWN flags (-O3 -march=native -fno-exceptions -fno-rtti, host libm; oracle/build_ref.sh).
+    The -march=native build is this repo's build container's; where the box's CPU cannot run it the x86-64-v3 twin is used."""
+    global _REF_BIN
+    if _REF_BIN:
+        return _REF_BIN
+    run_dir = os.path.join(ROOT, "assets", "run")
+    os.makedirs(run_dir, exist_ok=True)
+    for name in ("mrt_ref_native", "mrt_ref_v3", "mrt_ref"):
+        p = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(p):
+            continue
+        try:
+            r = subprocess.run([p, "stock", "-scene", "5", "-width", "32", "-height", "18", "-samples", "1", "-depth", "4", "-mode", "0", "-threads", "1"],
+                               cwd=run_dir, capture_output=True, text=True, timeout=60)
+            if r.returncode == 0:
+                _REF_BIN = (p, name)
+                return _REF_BIN
+        except Exception:
+            continue
+    raise RuntimeError("oracle/_ref/mrt_ref* missing or not runnable (built by __graft_entry__.build() where /root/reference exists)")
+
+
 def run_reference_cpu(scene, width, height, sample_spp, depth, threads):
     """The reference's own multithreaded CPU renderer (its main(), `-mode 0`), timed by its own clock
-    (main.cpp:375,394-405).  Test/benchmark infrastructure: oracle/_ref/mrt_ref."""
-    ref = os.path.join(ROOT, "oracle", "_ref", "mrt_ref")
-    run_dir = os.path.join(ROOT, "assets", "run")
-    if not os.path.exists(ref):
-        raise RuntimeError("oracle/_ref/mrt_ref is missing (built by __graft_entry__.build() where /root/reference exists)")
-    os.makedirs(run_dir, exist_ok=True)
-    out = subprocess.run([ref, "stock", "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(sample_spp),
-                          "-depth", str(depth), "-mode", "0", "-threads", str(threads)], cwd=run_dir, check=True, capture_output=True, text=True)
-    return json.loads(out.stdout.strip().splitlines()[-1])
+    (main.cpp:375,394-405).  Test/benchmark infrastructure under oracle/."""
+    binary, name = reference_binary()
+    out = subprocess.run([binary, "stock", "-scene", str(scene), "-width", str(width), "-height", str(height), "-samples", str(sample_spp),
+                          "-depth", str(depth), "-mode", "0", "-threads", str(threads)], cwd=os.path.join(ROOT, "assets", "run"), check=True,
+                         capture_output=True, text=True)
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["binary"] = name
+    return r
+
+
+def cpu_sample_spp(name, W, H, spp, want):
+    """Samples per pixel of the bounded CPU sample: `want` for the 1080p configs, fewer at 4K, the config's own spp if smaller."""
+    s = want if W * H <= 1920 * 1080 else max(4, want // 4)
+    return min(s, spp)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    scene, W, H, spp, depth, flop_per_ray = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_spp = args.cpu_spp
-    vals, rays_vals, secs = [], [], []
-    for i in range(args.warmup + args.steps):
-        r = run_reference_cpu(scene, W, H, sample_spp, depth, cores)
-        if i >= args.warmup:
-            vals.append(r["mpaths_per_s"]); rays_vals.append(r["mrays_per_s"]); secs.append(r["trace_seconds"])
-    v = sum(vals) / len(vals)
-    sample = f"{W}x{H}, {sample_spp} of {spp} spp per step (throughput is spp-independent), reference -mode 0 -threads {cores}"
+
+    def measure(name, steps, warmup):
+        scene, W, H, spp, depth = WORKLOADS[name]
+        sample_spp = cpu_sample_spp(name, W, H, spp, args.cpu_spp)
+        vals, rays_vals, secs, binary = [], [], [], ""
+        for i in range(warmup + steps):
+            r = run_reference_cpu(scene, W, H, sample_spp, depth, cores)
+            binary = r["binary"]
+            if i >= warmup:
+                vals.append(r["mpaths_per_s"]); rays_vals.append(r["mrays_per_s"]); secs.append(r["trace_seconds"])
+        sample = (f"{W}x{H}, {sample_spp} of {spp} spp per step (throughput is spp-independent), reference -mode 0 -threads {cores}, "
+                  f"binary {binary} (reference's own flags, host libm)")
+        return sum(vals) / len(vals), sum(rays_vals) / len(rays_vals) * 1e-3, 1000.0 * sum(secs) / len(secs), sample
+
+    name = args.workload
+    scene, W, H, spp, depth = WORKLOADS[name]
+    v, grays, ms, sample = measure(name, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "Mpath-samples/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (reference scene built from the reference's seed)",
-        "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "scene": scene, "width": W, "height": H, "spp": spp, "max_bounces": depth},
-        "grays_per_s": sum(rays_vals) / len(rays_vals) * 1e-3,
+        "config": config_dict(name, scene, W, H, spp, depth),
+        "grays_per_s": grays,
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_per_config:
+        per = {}
+        for other in WORKLOADS:
+            if other == name:
+                continue
+            ov, og, oms, osample = measure(other, 1, 0)
+            per[other] = {"value": ov, "unit": "Mpaths/s", "grays_per_s": og, "ms_per_step": oms, "steps": 1, "sample": osample,
+                          "config": config_dict(other, *WORKLOADS[other])}
+        line["per_config"] = per
     print(json.dumps(line))
     return 0
 
@@ -142,26 +198,84 @@ def scene_bytes(desc):
         int(d.n_image_bytes)
 
 
+class Workload:
+    """One BASELINE config on this rank: resident scene, bound accumulator, device-timed steps and an end-to-end step."""
+
+    def __init__(self, name, rank, world, local_rank, spp_override=0, size_override=""):
+        import torch
+        from miniraytracer_b200 import api, distributed as mdist
+        self.torch, self.api = torch, api
+        self.name, self.rank, self.world, self.local_rank = name, rank, world, local_rank
+        self.scene, self.W, self.H, self.spp, self.depth = WORKLOADS[name]
+        self.reduced = ""
+        if spp_override:
+            self.spp = spp_override
+            self.reduced = f" [REDUCED spp={self.spp}]"
+        if size_override:
+            self.W, self.H = (int(v) for v in size_override.lower().split("x"))
+            self.reduced += f" [REDUCED {self.W}x{self.H}]"
+        self.N = api.grid_samples(self.spp)
+        self.s_begin, self.s_end = mdist.shard_range(self.N, rank, world)
+        self.dev = torch.device("cuda", local_rank)
+        self.hs = api.HostScene(self.scene, self.W, self.H)
+        self.r = api.Renderer(self.hs, local_rank)
+        self.stream = torch.cuda.current_stream()
+        self.r.set_stream(self.stream.cuda_stream)
+        self.acc = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=self.dev)
+        self.final = torch.empty_like(self.acc)
+        self.r.bind_accumulator(self.acc.data_ptr(), self.W, self.H)
+        self.host_out = torch.empty((self.H, self.W, 4), dtype=torch.float32, pin_memory=True)
+        self.paths_per_step = self.W * self.H * self.N
+
+    def step_device(self, spp_slice=None):
+        """Hot path with the scene resident in HBM: render slice -> (all-reduce) -> finalize."""
+        import torch.distributed as dist
+        b, e = (self.s_begin, self.s_end) if spp_slice is None else spp_slice
+        self.r.render_async(self.W, self.H, self.spp, self.depth, sample_begin=b, sample_end=e)
+        if self.world > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        self.r.finalize_device(self.acc.data_ptr(), self.final.data_ptr(), self.W, self.H)
+
+    def step_e2e(self):
+        """Through the C ABI with HOST buffers: scene tables H2D (mrt_gpu_scene_upload) + render + reduce + finalize + frame D2H."""
+        import torch.distributed as dist
+        torch, api = self.torch, self.api
+        r2 = api.Renderer(self.hs, self.local_rank)
+        r2.set_stream(self.stream.cuda_stream)
+        r2.bind_accumulator(self.acc.data_ptr(), self.W, self.H)
+        r2.render_async(self.W, self.H, self.spp, self.depth, sample_begin=self.s_begin, sample_end=self.s_end)
+        if self.world > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        if self.rank == 0:
+            r2.finalize_device(self.acc.data_ptr(), self.final.data_ptr(), self.W, self.H)
+            self.host_out.copy_(self.final, non_blocking=True)
+        torch.cuda.synchronize()
+        r2.close()
+
+    def close(self):
+        self.r.close()
+        self.hs.close()
+        del self.acc, self.final, self.host_out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS), help="headline workload (default: BASELINE configs[1])")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling only; marks the line as reduced)")
     ap.add_argument("--size", default="", help="WxH override (profiling only; marks the line as reduced)")
-    ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample (a quarter of it at 4K)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="headline workload only")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-
-    from miniraytracer_b200 import api, distributed as mdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -174,25 +288,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert world == max(1, args.gpus) or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
-
-    scene, W, H, spp, depth, flop_per_ray = WORKLOADS[args.workload]
-    reduced = False
-    if args.spp:
-        spp, reduced = args.spp, True
-    if args.size:
-        W, H = (int(v) for v in args.size.lower().split("x"))
-        reduced = True
-    N = api.grid_samples(spp)
-    s_begin, s_end = mdist.shard_range(N, rank, world)
-
-    hs = api.HostScene(scene, W, H)
-    r = api.Renderer(hs, local_rank)
-    stream = torch.cuda.current_stream()
-    r.set_stream(stream.cuda_stream)
-    acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    final = torch.empty_like(acc)
-    r.bind_accumulator(acc.data_ptr(), W, H)
-    host_out = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    flops = alg_flop_per_ray()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -200,124 +296,161 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        """Hot path with the scene resident in HBM: render slice -> (all-reduce) -> finalize."""
-        r.render_async(W, H, spp, depth, sample_begin=s_begin, sample_end=s_end)
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-        r.finalize_device(acc.data_ptr(), final.data_ptr(), W, H)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    kernel_ms, rays_per_step = [], []
-    for _ in range(args.warmup):
-        step_device()
-        flush.zero_()
-    barrier()
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def measure(wl, steps, warmup, e2e_steps, warm_slice=None):
+        """Device-timed steps (CUDA events on the launch stream, L2 flushed between steps, max over ranks) + end-to-end steps."""
+        for _ in range(warmup):
+            wl.step_device(warm_slice)
+            flush.zero_()
+        barrier()
+        stream = wl.stream
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kernel_ms, rays, iters, coop = [], [], [], []
+        t0 = time.perf_counter()
+        for i in range(steps):
+            ev[i][0].record(stream)
+            wl.step_device()
+            ev[i][1].record(stream)
+            st = wl.r.stats()                    # waits for the render kernel of this step
+            kernel_ms.append(st["kernel_ms"]); rays.append(st["rays"]); iters.append(st["warp_iterations"])
+            coop.append((st["coop_trees"], st["coop_node_items"], st["coop_node_steps"], st["coop_leaf_items"], st["coop_leaf_steps"]))
+            flush.zero_()                        # L2 flush between timed steps (outside the event pairs)
+        barrier()
+        wall = time.perf_counter() - t0
+        total_s = reduce_max(sum(a.elapsed_time(b) for a, b in ev)) / 1000.0
+        rays_total = reduce_sum(float(sum(rays)))
+        res = {
+            "value": wl.paths_per_step * steps / total_s / 1e6, "ms_per_step": 1000.0 * total_s / steps,
+            "grays_per_s": rays_total / total_s / 1e9, "rays_per_path": rays_total / (wl.paths_per_step * steps),
+            "kernel_ms": sum(kernel_ms) / len(kernel_ms), "rays_per_launch": sum(rays) / len(rays),
+            "live_lane_frac": sum(rays) / max(1.0, 32.0 * sum(iters)), "wall_s": wall, "steps": steps, "warmup": warmup,
+        }
+        if coop[-1][0]:
+            c = coop[-1]
+            res["coop_trees"] = {"node_step_fill": c[1] / max(1.0, 32.0 * c[2]), "leaf_step_fill": c[3] / max(1.0, 32.0 * c[4])}
+        if e2e_steps:
+            wl.step_e2e()                        # warm (pool / pinned buffers are cached per process)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                wl.step_e2e()
+            barrier()
+            e2e_s = reduce_max(time.perf_counter() - t0)
+            res["e2e"] = {"value": wl.paths_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes(wl.hs.desc),
+                          "d2h_bytes_per_step": wl.W * wl.H * 16, "steps": e2e_steps,
+                          "image_mean": float(wl.host_out[..., :3].double().mean()) if rank == 0 else None}
+        return res
+
+    def roofline_of(name, res, sm_count, max_mhz, peaks, clocks=None):
+        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * max_mhz * 1e6 / 1e12
+        achieved = res["rays_per_launch"] * flops[name] / (res["kernel_ms"] * 1e-3) / 1e12
+        out = {
+            "bound": "fp32",   # SM issue / FP32 pipe (north_star): not a dense contraction, scene is cache resident, HBM nearly idle
+            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+            "peak_source": (f"{sm_count} SMs x 128 FP32 lanes x 2 x {max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; no measured FP32 "
+                            "figure exists there)") if peaks else "fallback 1965 MHz (MEASURED_PEAKS.json absent)",
+            "alg_flop_per_ray": flops[name], "alg_flop_source": "tools/alg_flops.py (operation counters of the reference algorithm x SURVEY 8d weights)",
+            "rays_per_launch": res["rays_per_launch"], "kernel_ms": res["kernel_ms"],
+        }
+        if clocks and clocks.get("sm_mhz"):
+            out["frac_at_clock_under_load"] = achieved / (fp32_peak * clocks["sm_mhz"] / max_mhz)
+        return out
+
+    # ---------------------------------------------------------------- headline
+    head = Workload(args.workload, rank, world, local_rank, args.spp, args.size)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        ev[i][0].record(stream)
-        step_device()
-        ev[i][1].record(stream)
-        st = r.stats()                       # waits for the render kernel of this step
-        kernel_ms.append(st["kernel_ms"]); rays_per_step.append(st["rays"])
-        flush.zero_()                        # L2 flush between timed steps (outside the event pairs)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    hres = measure(head, args.steps, args.warmup, max(1, min(args.steps, 3)))
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    rays_t = torch.tensor([float(sum(rays_per_step))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
-    total_s = float(total_ms.item()) / 1000.0
-    paths_per_step = W * H * N
-    value = paths_per_step * args.steps / total_s / 1e6
-    grays = float(rays_t.item()) / total_s / 1e9
+    sm_count = head.r.info.sm_count
+    peaks = measured_peaks()
+    max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
 
-    # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + reduce + readback (D2H)
-    desc_bytes = scene_bytes(hs.desc)
-    e2e_steps = max(1, min(args.steps, 3))
-
-    def step_e2e():
-        r2 = api.Renderer(hs, local_rank)                  # mrt_gpu_scene_upload: host tables -> device
-        r2.set_stream(stream.cuda_stream)
-        r2.bind_accumulator(acc.data_ptr(), W, H)
-        r2.render_async(W, H, spp, depth, sample_begin=s_begin, sample_end=s_end)
-        if world > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            r2.finalize_device(acc.data_ptr(), final.data_ptr(), W, H)
-            host_out.copy_(final, non_blocking=True)        # D2H of the finished frame into pinned memory
-        torch.cuda.synchronize()
-        r2.close()
-
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = paths_per_step * e2e_steps / float(e2e_s.item()) / 1e6
-    checksum = float(host_out[..., :3].double().mean())
-
+    line = None
     if rank == 0:
-        peaks = measured_peaks()
-        sm_count = r.info.sm_count
-        max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
-        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * max_mhz * 1e6 / 1e12
-        k_ms = sum(kernel_ms) / len(kernel_ms)
-        k_rays = sum(rays_per_step) / len(rays_per_step)
-        achieved = k_rays * flop_per_ray / (k_ms * 1e-3) / 1e12
-        roofline = {
-            "bound": "fp32",   # SM issue / FP32 pipe (north_star): not a dense contraction, scene is L2-resident
-            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-            "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x {max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
-                           "no measured FP32 figure exists there)" if peaks else "fallback 1965 MHz (MEASURED_PEAKS.json absent)",
-            "alg_flop_per_ray": flop_per_ray, "rays_per_launch": k_rays, "kernel_ms": k_ms,
-            "kernel": "render_pixel_binned<cornell, 6 blocks/SM>" if args.workload == "C2" else "render_pixel_binned",
-            "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload) if not reduced else None,
-            "issue_slots_frac_est": (k_rays * NCU_WARP_INST_PER_RAY[args.workload] / (k_ms * 1e-3) / (sm_count * 4 * max_mhz * 1e6))
-            if args.workload in NCU_WARP_INST_PER_RAY else None,
-            "note": "bound = SM instruction issue on divergent code (ncu r1k: issue slots 68 % busy at 6 warps per scheduler, 22.8 of 32 "
-                    "lanes active per instruction, FP32 pipe 23 %; HBM 55 GB per launch = 175 GB/s, almost all of it the 16 B per path of "
-                    "the sample staging array, the path pool lives in L2); 'achieved' counts the reference algorithm's flops per ray "
-                    "(SURVEY 8d)",
-            "frac_at_clock_under_load": (achieved / (fp32_peak * clocks["sm_mhz"] / max_mhz)) if clocks and clocks.get("sm_mhz") else None,
-        }
+        roof = roofline_of(args.workload, hres, sm_count, max_mhz, peaks, clocks)
+        roof["kernel"] = "render_pixel_binned<cornell, 6 blocks/SM>" if args.workload == "C2" else "render_pixel_binned"
+        # DRAM traffic of the dominant kernel: from ONE ncu --set full capture of this workload on one GPU (profiles/), not a
+        # measurement of this run -- so only reported for the full-size single-GPU line
+        traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        traffic = None
+        if world == 1 and not head.reduced and os.path.exists(traffic_file):
+            traffic = json.load(open(traffic_file)).get(args.workload)
+        roof["traffic"] = traffic["dram_bytes_per_launch"] if traffic else None
+        roof["traffic_source"] = ("from_ncu_capture: " + traffic["capture"]) if traffic else None
+        roof["note"] = ("bound = SM instruction issue on divergent code; 'achieved' counts the reference algorithm's flops per ray "
+                        "(SURVEY 8d); the scene is L1/L2 resident, HBM carries the accumulator and the sample staging only")
         line = {
-            "metric": "Mpath-samples/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": "Mpath-samples/s", "value": hres["value"], "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": hres["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (reference scene rebuilt from the reference's seed; no external data)",
-            "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload] + (" [REDUCED %dx%d spp=%d]" % (W, H, spp) if reduced else ""),
-                       "scene": scene, "width": W, "height": H, "spp": N, "max_bounces": depth, "parallelism": f"spp-sharded x{world}",
-                       "l2": "256 MB memset between timed steps; scene tables (<1 MB) are cache resident by design"},
-            "grays_per_s": grays, "rays_per_path": float(rays_t.item()) / (paths_per_step * args.steps),
-            "wall_s_timed_region": t_wall,
-            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes, "d2h_bytes_per_step": W * H * 16,
-                    "steps": e2e_steps, "image_mean": checksum},
+            "config": config_dict(args.workload, head.scene, head.W, head.H, head.N, head.depth),
+            "reduced": head.reduced or None,
+            "parallelism": f"spp-sharded x{world}",
+            "l2": "256 MB memset between timed steps; scene tables (<1 MB) are cache resident by design",
+            "grays_per_s": hres["grays_per_s"], "rays_per_path": hres["rays_per_path"], "live_lane_frac": hres["live_lane_frac"],
+            "wall_s_timed_region": hres["wall_s"],
+            "e2e": hres["e2e"],
             "gpu_launches": args.steps * 2,   # render kernel + finalize kernel per step (NCCL's kernels not counted)
-            "roofline": roofline,
+            "roofline": roof,
             "clocks": clocks,
         }
+    head.close()
+
+    # ---------------------------------------------------------------- the other BASELINE configs
+    if not args.no_per_config and not args.spp and not args.size:
+        per = {}
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            spp_override = 0
+            if name == "C5" and world < 8:
+                spp_override = {1: 256, 2: 576, 4: 1024}.get(world, 256)   # 4K x 4096 spp is ~75 s per frame on one GPU: reduced and SAID so (full on 8 GPUs)
+            wl = Workload(name, rank, world, local_rank, spp_override)
+            heavy = wl.paths_per_step > 3e9
+            # heavy configs: one timed step; the warm-up renders a 64-sample slice (kernel and caches warm, clocks up)
+            warm_slice = (wl.s_begin, min(wl.s_end, wl.s_begin + 64)) if heavy else None
+            res = measure(wl, 1 if heavy else 3, 1 if heavy else 2, 1, warm_slice)
+            if rank == 0:
+                entry = {"value": res["value"], "unit": "Mpaths/s", "grays_per_s": res["grays_per_s"], "kernel_ms": res["kernel_ms"],
+                         "ms_per_step": res["ms_per_step"], "rays_per_path": res["rays_per_path"], "lanes": res["live_lane_frac"],
+                         "lanes_note": "share of lanes with a live path per segment step (mrt_gpu_stats.warp_iterations); lanes per instruction are in profiles/",
+                         "roofline": {k: v for k, v in roofline_of(name, res, sm_count, max_mhz, peaks).items()
+                                      if k in ("achieved", "peak", "frac", "alg_flop_per_ray", "unit")},
+                         "e2e": res["e2e"], "steps": res["steps"], "warmup": res["warmup"],
+                         "config": config_dict(name, wl.scene, wl.W, wl.H, wl.N, wl.depth), "reduced": wl.reduced or None}
+                if "coop_trees" in res:
+                    entry["coop_trees"] = res["coop_trees"]
+                per[name] = entry
+            wl.close()
+        if rank == 0:
+            line["per_config"] = per
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cores = os.cpu_count() or 1
-                cb = run_reference_cpu(scene, W, H, args.cpu_spp, depth, cores)
+                scene, W, H, spp, depth = WORKLOADS[args.workload]
+                cb = run_reference_cpu(scene, head.W, head.H, args.cpu_spp, depth, cores)
                 line["cpu_baseline"] = {"value": cb["mpaths_per_s"], "unit": "Mpaths/s", "cores": cores, "kind": "reference",
                                         "grays_per_s": cb["mrays_per_s"] * 1e-3,
-                                        "sample": f"{W}x{H}, {args.cpu_spp} of {N} spp, reference -mode 0 -threads {cores}, {cb['trace_seconds']:.1f} s"}
+                                        "sample": f"{head.W}x{head.H}, {args.cpu_spp} of {head.N} spp, reference -mode 0 -threads {cores}, "
+                                                  f"{cb['trace_seconds']:.1f} s, binary {cb['binary']} (reference's own flags, host libm)"}
             except Exception as e:   # the baseline is reported, never substituted
                 line["cpu_baseline"] = {"value": None, "unit": "Mpaths/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))
-    r.close()
-    hs.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -64,7 +64,11 @@ void mrt_params_default(MrtParams *p);
 int mrt_params_parse(int argc, char **argv, MrtParams *p);
 
 typedef struct MrtHostScene MrtHostScene;
-/* scene: the reference's enum scenes value (scene.h:6-17), aspect = width/height. */
+/* The Cornell box and the final scene allocate a light list of two objects -- the ceiling light and a glass sphere -- but pass
+ * count 1 (scene.cpp:326-329, 456-459), so only the rect is importance-sampled.  OR-ing this flag into `scene` builds the list
+ * with both (the sphere then goes through sphere::pdf_value / pdf_generate, sphere.cpp:63-79).  Default = the reference's count. */
+#define MRT_SCENE_ALL_LIGHTS 0x100u
+/* scene: the reference's enum scenes value (scene.h:6-17), optionally | MRT_SCENE_ALL_LIGHTS; aspect = width/height. */
 int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHostScene **out);
 /* Flattened description (pointers stay valid until mrt_scene_free). */
 const MrtSceneDesc *mrt_scene_desc(const MrtHostScene *s);
@@ -155,6 +159,9 @@ int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize);
 /* Adaptive logarithmic tone map + ARGB32 pack of the reference's preview loop
  * (main.cpp:416-444, vec3.h:327-333) from the finalised image; argb_host: width*height uint32. */
 int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host);
+/* The same tone map on device buffers: img_dev = width*height float4 (finalised linear image), argb_dev = width*height
+ * uint32; asynchronous on the scene's stream. */
+int mrt_gpu_tonemap_device(MrtScene *s, const void *img_dev, void *argb_dev, uint32_t width, uint32_t height);
 /* Requests the running render to stop early (G_isRunning = false, main.cpp:274). */
 int mrt_gpu_cancel(MrtScene *s);
 void mrt_gpu_destroy(MrtScene *s);

@@ -82,6 +82,7 @@ class RenderStats(C.Structure):
 
 
 MRT_RENDER_ACCUMULATE = 1
+SCENE_ALL_LIGHTS = 0x100   # MRT_SCENE_ALL_LIGHTS: light list with both allocated entries (ceiling light + glass sphere)
 DEFAULT_SEED = 11350390909718046443  # main.cpp:302
 
 # every symbol include/mrt_gpu.h declares
@@ -89,7 +90,7 @@ EXPORTS = [
     "mrt_last_error", "mrt_params_default", "mrt_params_parse", "mrt_scene_create", "mrt_scene_desc",
     "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_tuning", "mrt_gpu_set_stream",
     "mrt_gpu_bind_accumulator", "mrt_gpu_render_async", "mrt_gpu_poll", "mrt_gpu_wait", "mrt_gpu_stats",
-    "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_cancel", "mrt_gpu_destroy",
+    "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_tonemap_device", "mrt_gpu_cancel", "mrt_gpu_destroy",
 ]
 
 
@@ -140,6 +141,7 @@ def load(build_if_missing=True):
     lib.mrt_gpu_finalize_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_float]
     lib.mrt_gpu_readback.argtypes = [vp, vp, C.c_int]
     lib.mrt_gpu_tonemap.argtypes = [vp, vp]
+    lib.mrt_gpu_tonemap_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32]
     lib.mrt_gpu_cancel.argtypes = [vp]
     lib.mrt_gpu_destroy.argtypes = [vp]
     lib.mrt_gpu_destroy.restype = None
@@ -185,7 +187,7 @@ class HostScene:
         aspect = np.float32(width) / np.float32(height)
         _check(lib.mrt_scene_create(int(scene), C.c_float(aspect), (asset_dir or default_asset_dir()).encode(),
                                     C.byref(self._h)))
-        self.scene = int(scene)
+        self.scene = int(scene)   # may carry SCENE_ALL_LIGHTS
 
     @classmethod
     def load(cls, path):
@@ -290,6 +292,9 @@ class Renderer:
         out = np.empty((h, w), dtype=np.uint32)
         _check(self._lib.mrt_gpu_tonemap(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def tonemap_device(self, img_ptr, argb_ptr, width, height):
+        _check(self._lib.mrt_gpu_tonemap_device(self._h, C.c_void_p(img_ptr), C.c_void_p(argb_ptr), width, height))
 
     def cancel(self):
         _check(self._lib.mrt_gpu_cancel(self._h))

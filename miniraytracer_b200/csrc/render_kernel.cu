@@ -712,6 +712,17 @@ extern "C" int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize) {
     return MRT_OK;
 }
 
+extern "C" int mrt_gpu_tonemap_device(MrtScene *s, const void *img_dev, void *argb_dev, uint32_t width, uint32_t height) {
+    if (!s || !img_dev || !argb_dev) { set_error("mrt_gpu_tonemap_device: null argument"); return MRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const uint32_t n = width * height;
+    CUDA_TRY(cudaMemsetAsync(s->max_bits, 0, sizeof(unsigned int), s->stream));
+    max_luminance_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>((const float4 *) img_dev, n, s->max_bits);
+    tonemap_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>((const float4 *) img_dev, (uint32_t *) argb_dev, n, s->max_bits);
+    CUDA_TRY(cudaGetLastError());
+    return MRT_OK;
+}
+
 extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
     if (!s || !argb_host) { set_error("mrt_gpu_tonemap: null argument"); return MRT_E_INVALID; }
     if (!s->rendered) { set_error("mrt_gpu_tonemap: nothing rendered yet"); return MRT_E_STATE; }
@@ -721,10 +732,8 @@ extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
     if (rc) return rc;
     rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->max_bits, 0, sizeof(unsigned int), s->stream));
-    max_luminance_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(s->final_buf, (uint32_t) n, s->max_bits);
-    tonemap_kernel<<<((uint32_t) n + 255) / 256, 256, 0, s->stream>>>(s->final_buf, s->argb_buf, (uint32_t) n, s->max_bits);
-    CUDA_TRY(cudaGetLastError());
+    rc = mrt_gpu_tonemap_device(s, s->final_buf, s->argb_buf, s->last_w, s->last_h);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(argb_host, s->argb_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return MRT_OK;

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "mrt_types.h"
+#include "mrt_gpu.h"
 
 namespace mrt {
 
@@ -158,7 +158,7 @@ struct PerlinTables {
 const PerlinTables &perlin_tables();
 
 // scenes (scene.cpp) -- `scene` uses the reference's enum values (scene.h:6-17)
-bool build_scene(SceneGraph &g, uint32_t scene, float aspect, const std::string &asset_dir);
+bool build_scene(SceneGraph &g, uint32_t scene_and_flags, float aspect, const std::string &asset_dir);   // flags: MRT_SCENE_ALL_LIGHTS (mrt_gpu.h)
 
 // obj_loader.cpp restated; M4 is the reference's column-major Mat4 (mat4.h), c[col][row]
 struct M4 {

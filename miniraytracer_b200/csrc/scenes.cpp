@@ -150,7 +150,7 @@ static bool earth(SceneGraph &g, float aspect, const std::string &assets) {   //
     return true;
 }
 
-static bool cornell_box(SceneGraph &g, float aspect) {   // scene.cpp:283-332
+static bool cornell_box(SceneGraph &g, float aspect, bool all_lights) {   // scene.cpp:283-332
     g.camera = cornell_camera(aspect, 0.0f);
     int red = g.lambertian(g.color_tex(H3(0.65f, 0.055f, 0.06f)));
     int white = g.lambertian(g.color_tex(H3(0.73f, 0.73f, 0.73f)));
@@ -169,8 +169,8 @@ static bool cornell_box(SceneGraph &g, float aspect) {   // scene.cpp:283-332
     int s = g.sphere(H3(190, 90, 190), 90, glass);
     l.push_back(s);
     g.objects = g.list(l, 0.0f, 1.0f);
-    // the array holds {light, sphere} but the list is built with count 1 (scene.cpp:326-329)
-    g.biased = g.list(std::vector<int>{lrect}, 0.0f, 1.0f);
+    // the array holds {light, sphere} but the list is built with count 1 (scene.cpp:326-329); MRT_SCENE_ALL_LIGHTS uses both
+    g.biased = all_lights ? g.list(std::vector<int>{lrect, s}, 0.0f, 1.0f) : g.list(std::vector<int>{lrect}, 0.0f, 1.0f);
     return true;
 }
 
@@ -197,7 +197,7 @@ static bool cornell_smoke(SceneGraph &g, float aspect) {   // scene.cpp:334-378
     return true;
 }
 
-static bool book2_final(SceneGraph &g, HostRng &rng, float aspect, const std::string &assets) {   // scene.cpp:380-462
+static bool book2_final(SceneGraph &g, HostRng &rng, float aspect, const std::string &assets, bool all_lights) {   // scene.cpp:380-462
     H3 cam_pos(450, 278, -560), lookat(200, 278, 300), up(0, 1, 0);
     float focus_dist = hlength(cam_pos - lookat);
     g.camera = Camera(cam_pos, lookat, up, 40.0f, aspect, 0.0f, focus_dist, 0.0f, 1.0f);
@@ -230,7 +230,8 @@ static bool book2_final(SceneGraph &g, HostRng &rng, float aspect, const std::st
     l.push_back(lo);
     H3 center(400, 400, 200);
     l.push_back(g.sphere(center, 50, orange, center + H3(30, 0, 0), 0, 1));
-    l.push_back(g.sphere(H3(260, 150, 45), 50, g.dielectric(1.5f)));
+    const int gs = g.sphere(H3(260, 150, 45), 50, g.dielectric(1.5f));
+    l.push_back(gs);
     l.push_back(g.sphere(H3(0, 150, 145), 50, g.metal(g.color_tex(H3(0.8f, 0.8f, 0.9f)), 0.1f)));
     l.push_back(g.sphere(H3(400, 200, 400), 100, earth));
     l.push_back(g.sphere(H3(220, 280, 300), 80, perlin));
@@ -246,7 +247,8 @@ static bool book2_final(SceneGraph &g, HostRng &rng, float aspect, const std::st
     }
     l.push_back(g.translate(g.rotate_y(g.bvh(spherelist, 0, spherelist.size(), 0.0f, 1.0f), 15), H3(-100, 270, 395)));
     g.objects = g.list(l, 0.0f, 1.0f);
-    g.biased = g.list(std::vector<int>{lo}, 0.0f, 1.0f);   // {light, glass sphere} with count 1 (scene.cpp:456-459)
+    // {light, glass sphere} with count 1 (scene.cpp:456-459); MRT_SCENE_ALL_LIGHTS uses both
+    g.biased = all_lights ? g.list(std::vector<int>{lo, gs}, 0.0f, 1.0f) : g.list(std::vector<int>{lo}, 0.0f, 1.0f);
     return true;
 }
 
@@ -281,7 +283,9 @@ static bool triangles(SceneGraph &g, float aspect, const std::string &assets) { 
     return true;
 }
 
-bool build_scene(SceneGraph &g, uint32_t scene, float aspect, const std::string &asset_dir) {
+bool build_scene(SceneGraph &g, uint32_t scene_and_flags, float aspect, const std::string &asset_dir) {
+    const uint32_t scene = scene_and_flags & 0xFFu;
+    const bool all_lights = (scene_and_flags & MRT_SCENE_ALL_LIGHTS) != 0;
     HostRng rng;
     rng.seed(11350390909718046443uLL, 6305599193148252115uLL);   // main.cpp:302
     g.sky = scene < 5;                                            // main.cpp:110
@@ -291,9 +295,9 @@ bool build_scene(SceneGraph &g, uint32_t scene, float aspect, const std::string 
     case 2: return two_spheres(g, aspect);
     case 3: return spheres_perlin(g, aspect);
     case 4: return earth(g, aspect, asset_dir);
-    case 5: return cornell_box(g, aspect);
+    case 5: return cornell_box(g, aspect, all_lights);
     case 6: return cornell_smoke(g, aspect);
-    case 7: return book2_final(g, rng, aspect, asset_dir);
+    case 7: return book2_final(g, rng, aspect, asset_dir, all_lights);
     case 8: return triangles(g, aspect, asset_dir);
     default: g.error = "unknown scene"; return false;
     }

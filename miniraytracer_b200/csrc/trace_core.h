@@ -35,6 +35,20 @@
 
 namespace mrt {
 
+// Algorithmic operation counters (op counts of the REFERENCE algorithm, from which the roofline's
+// flop per ray is derived -- tools/alg_flops.py).  Compiled in only by the test-side host emulation
+// (tests/host_emul/emul_render.cpp defines MRT_COUNT_OPS and owns the thread-local `mrt_ops`); nothing on the device.
+#if defined(MRT_COUNT_OPS) && !defined(__CUDACC__)
+struct OpCounts {
+    unsigned long long paths, ray_ctor, rng, sphere_hit, sphere_moving, rect_hit, tri_hit, translate, rotate, lambert, metal, dielectric,
+        isotropic, lightpdf, perlin, image, checker, sky;
+};
+extern thread_local OpCounts mrt_ops;
+#define MRT_OP(x) (mrt::mrt_ops.x++)
+#else
+#define MRT_OP(x) ((void) 0)
+#endif
+
 // Scene-feature specialisation.  Every function below that takes a `feat` argument is force-inlined into a
 // kernel instantiated for a compile-time constant mask (MRT_FEAT_* in mrt_types.h); code for object classes,
 // materials and textures the scene does not contain is removed by constant folding, which shortens the
@@ -141,7 +155,7 @@ MRT_HD void rng_seed(Rng &r, uint64_t initstate, uint64_t initseq) {
     r.state += initstate;
     rng_next(r);
 }
-MRT_HD float randf(Rng &r) { return u2f(0x3f800000u | (rng_next(r) & 0x007FFFFFu)) - 1.0f; }
+MRT_HD float randf(Rng &r) { MRT_OP(rng); return u2f(0x3f800000u | (rng_next(r) & 0x007FFFFFu)) - 1.0f; }
 // pcg.cpp:70-77 (draw order x, y, z)
 MRT_HD V3 random_in_sphere(Rng &r) {
     V3 p;
@@ -200,12 +214,14 @@ MRT_HD uint32_t dir_mask(V3 d) {
     return 1u << (Z | (Y << 1) | (X << 2));
 }
 MRT_FN void ray_set_dir(Ray &r, V3 dir) {  // direction is normalised by the ctor (ray.h:30)
+    MRT_OP(ray_ctor);
     r.d = normalize(dir);
     r.inv = v3(frcp(r.d.x), frcp(r.d.y), frcp(r.d.z));
     r.mask = dir_mask(r.d);
 }
 // ray for a primitive self-test (pdf_value): only origin + normalised direction are used
 MRT_HD Ray make_probe_ray(V3 o, V3 dir, float time) {
+    MRT_OP(ray_ctor);
     Ray r;
     r.o = o;
     r.time = time;
@@ -300,6 +316,7 @@ struct Counters {   // optional algorithmic op counters
 // ----------------------------------------------------------- primitive tests
 MRT_HD V3 sphere_center(const MrtF4 &s0, const MrtF4 &s1, const MrtF4 *tab, uint32_t idx, float time) {
     if (f2u(s1.w) >> 31) {  // isMoving, sphere.h:24-31
+        MRT_OP(sphere_moving);
         MrtF4 s2 = ld4(tab, 3 * idx + 2);
         float k = fdiv(time - s2.x, s2.y - s2.x);
         return v3(s0) + k * (v3(s1) - v3(s0));
@@ -330,6 +347,7 @@ MRT_FN bool hit_sphere(const uint32_t feat, const SceneView &sc, uint32_t idx, c
             ok = (t < tmax && t > tmin);
         }
         if (ok) {
+            MRT_OP(sphere_hit);
             rec.t = t;
             if (full) {
                 uint32_t mat = f2u(s1.w) & 0x7FFFFFFFu;
@@ -358,6 +376,7 @@ MRT_HD bool hit_rect(const uint32_t feat, const SceneView &sc, uint32_t axis, ui
     float a = oa + t * da;
     float b = ob + t * db;
     if (a < q0.x || a > q0.y || b < q0.z || b > q0.w) return false;
+    MRT_OP(rect_hit);
     rec.t = t;
     if (full) {
         rec.mat = f2u(q1.z);
@@ -391,6 +410,7 @@ MRT_FN bool hit_triangle(const SceneView &sc, uint32_t idx, const Ray &r, float 
     float invDet = frcp(det);
     float t = dot(v, qvec) * invDet * sign;
     if ((t < tmin) | (t > tmax)) return false;
+    MRT_OP(tri_hit);
     rec.t = t;
     if (full) {
         uu *= invDet;
@@ -540,6 +560,7 @@ MRT_HD bool isect_run(const uint32_t feat, const SceneView &sc, Ray &ray, Isect 
                     r2 = r0;
                 }
                 if (cnt) cnt->xform++;
+                if (type == MRT_T_ROTATE_Y) MRT_OP(rotate); else MRT_OP(translate);
                 st.pushf(ray.o.x); st.pushf(ray.o.y); st.pushf(ray.o.z);
                 st.pushf(ray.d.x); st.pushf(ray.d.y); st.pushf(ray.d.z);
                 st.pushf(ray.inv.x); st.pushf(ray.inv.y); st.pushf(ray.inv.z);
@@ -692,6 +713,7 @@ MRT_HD bool intersect(const uint32_t feat, const SceneView &sc, Ray &ray, float 
 // ------------------------------------------------------------------- textures
 // texture.cpp:68-165
 MRT_HD float perlin_noise(const SceneView &sc, V3 p) {
+    MRT_OP(perlin);
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     float u = p.x - fx, v = p.y - fy, w = p.z - fz;
     int i = (int) fx, j = (int) fy, k = (int) fz;
@@ -735,6 +757,7 @@ MRT_FN V3 tex_sample(const uint32_t feat, const SceneView &sc, uint32_t tex, flo
         uint32_t kind = f2u(t.x);
         if (!MRT_HAS(feat, MRT_FEAT_TEX) || kind == MRT_X_COLOR) return v3(t.y, t.z, t.w);   // color_tex only
         if (kind == MRT_X_CHECKER) {   // texture.cpp:7-13
+            MRT_OP(checker);
             float s = t.w;
             float sines = 1.0f;
 #ifdef __CUDA_ARCH__
@@ -752,6 +775,7 @@ MRT_FN V3 tex_sample(const uint32_t feat, const SceneView &sc, uint32_t tex, flo
             return v3(1, 1, 1) * turb;
         }
         // image, texture.cpp:207-225
+        MRT_OP(image);
         int32_t width = (int32_t) f2u(t.y), height = (int32_t) f2u(t.z);
         int32_t i = (int32_t) (u * width);
         int32_t j = (int32_t) ((1 - v) * height);
@@ -768,6 +792,7 @@ MRT_FN V3 tex_sample(const uint32_t feat, const SceneView &sc, uint32_t tex, flo
 // (scene_object.h:64-77); sphere (sphere.cpp:63-79) and xz_rect (rect.cpp:92-107)
 // have pdfs, every other object the base-class defaults (scene_object.h:24-29).
 MRT_FN float light_pdf_value(const uint32_t feat, const SceneView &sc, V3 origin, V3 dir, float time) {
+    MRT_OP(lightpdf);
     float sum = 0;
     // every light builds the same probe ray (ray ctor: normalise once more, ray.h:30) -- hoisted out of the loop
     Ray r = make_probe_ray(origin, dir, time);
@@ -859,6 +884,7 @@ struct Path {
 // A: camera::get_ray (camera.h:38-45) for sample s of pixel (x, y); regular sub-pixel grid (main.cpp:319-332,156-157)
 MRT_HD void path_begin(const SceneView &sc, Path &p, Rng &rng, uint32_t x, uint32_t y, uint32_t s, uint32_t sqrt_n,
                        uint32_t width, uint32_t height, uint64_t seed) {
+    MRT_OP(paths);
     uint64_t stream = ((uint64_t) y * width + x) * ((uint64_t) sqrt_n * sqrt_n) + s;
     rng_seed(rng, seed, stream);
     uint32_t i = s / sqrt_n, j = s - i * sqrt_n;
@@ -912,6 +938,7 @@ MRT_HD void path_advance(const uint32_t feat, const SceneView &sc, Path &p) {
 MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool hit, const Hit &rec, uint32_t max_bounces, Rng &rng) {
     if (!hit) {   // main.cpp:108-117
         if (sc.sky) {
+            MRT_OP(sky);
             float t = 0.5f * (p.ray.d.y + 1.0f);
             float a = 1.0f - t;
             V3 bg = v3(a, a, a) + t * v3(0.5f, 0.7f, 1.0f);
@@ -939,9 +966,11 @@ MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool h
         float dp = 2.0f * dot(r.d, rec.n);          // reflect(), vec3.h:178-181
         dir = r.d - (dp * rec.n);
         if (is_metal) {                             // material.h:84-98
+            MRT_OP(metal);
             dir = dir + (1 - m.z) * random_in_sphere(rng);
             p.T = texv * p.T;
         } else {                                    // material.h:106-175
+            MRT_OP(dielectric);
             float ref_index = m.z;
             V3 fn;
             float ni_over_nt;
@@ -971,6 +1000,7 @@ MRT_HD bool path_shade(const uint32_t feat, const SceneView &sc, Path &p, bool h
         // lambertian (material.h:40-53) / isotropic (material.h:64-73): direction from the mixture pdf
         // (main.cpp:84-92); its weight needs the NORMALISED direction and is applied in path_advance
         const bool lambert = !MRT_HAS(feat, MRT_FEAT_VOLUMES) || (kind == MRT_M_LAMBERTIAN);
+        if (lambert) MRT_OP(lambert); else MRT_OP(isotropic);
         bool use_light = false;
         if (sc.n_lights) use_light = randf(rng) < 0.5f;   // mix_pdf::generate, pdf.h:74-79
         if (use_light) {

@@ -37,6 +37,23 @@ done
 # -ffp-contract=off: no FMA contraction, so results do not depend on the optimiser.
 g++ -std=c++20 -O3 -march=x86-64-v3 -ffp-contract=off -fno-exceptions -fpermissive \
     -D__cdecl= -D__stdcall= -w -I"$SRC/include" -I"$TMP" $FILES "$TMP/cr_libm.o" -o "$OUT/mrt_ref" -lpthread -ldl
+# CPU-baseline binaries: the reference as it would actually run -- its own flags (clang/clang_build_linux.sh:23-29:
+# -std=c++20 -O3 -march=native -fno-exceptions -fno-rtti), the host libm, no interposer, the compiler's default
+# floating-point contraction.  Used ONLY for timing (bench.py --impl reference and cpu_baseline); parity uses mrt_ref above.
+# -march=native is this container's CPU; the x86-64-v3 twin is the fallback where the GPU box's host CPU lacks an
+# instruction set (bench.py probes the native binary first).
+TFILES=""
+for f in "$TMP"/*.cpp; do
+    case "$(basename "$f")" in
+        main.cpp) ;;
+        *) TFILES="$TFILES $f" ;;
+    esac
+done
+for variant in native x86-64-v3; do
+    out="$OUT/mrt_ref_native"; [ "$variant" = "x86-64-v3" ] && out="$OUT/mrt_ref_v3"
+    g++ -std=c++20 -O3 -march=$variant -fno-exceptions -fno-rtti -fpermissive -DMRT_REF_TIMING_ONLY \
+        -D__cdecl= -D__stdcall= -w -I"$SRC/include" -I"$TMP" $TFILES -o "$out" -lpthread
+done
 # assets (data, not source)
 cp -f "$SRC/earthmap.jpg" "$ASSETS/earthmap.jpg"
 for o in bunny.obj Teapot3_no_vt.obj teapot.obj simple.obj pyramid.obj cylinder.obj; do

@@ -19,14 +19,17 @@
 //
 // usage:
 //   mrt_ref render -scene S -width W -height H -samples N -depth D -seed X
-//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] -out file.bin
+//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] [-lights all] -out file.bin
 //                  (crop window: only those pixels of the W x H frame are traced; stream ids and u,v stay the
 //                   full frame's, so BASELINE.json's full-size configurations can be spot-checked in seconds)
-//   mrt_ref stock  <reference command line>  [-dump file.bin]
+//   mrt_ref stock  <reference command line>  [-dump file.bin] [-dumpargb file.u32]   (final linear frame / its tone map)
 //   mrt_ref dump-scene -scene S -width W -height H -out file.txt
 //   mrt_ref kat
 //   mrt_ref dump-image out.ppm          (decodes ../earthmap.jpg via the
 //                                        reference's vendored stb_image)
+// Built twice by build_ref.sh: mrt_ref (parity: -ffp-contract=off, portable -march, canonical libm interposed at link time)
+// and mrt_ref_native / mrt_ref_v3 (-DMRT_REF_TIMING_ONLY: render + stock only, the reference's OWN build flags
+// clang/clang_build_linux.sh:23-29 = -O3 -march=native -fno-exceptions -fno-rtti, host libm) for the CPU baseline.
 // The process must be started with cwd = <assets>/run (the reference opens
 // "../earthmap.jpg" and "../obj/*.obj", scene.cpp:139,503,509).
 #include <atomic>
@@ -44,7 +47,9 @@
 #include "main.cpp"
 #undef main
 
+#ifndef MRT_REF_TIMING_ONLY
 #include "stb_image.h"
+#endif
 
 extern bool MRT_headless_quiet;
 const char *MRT_headless_last_title();
@@ -57,6 +62,7 @@ extern int *pz;
 
 static uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
+#ifndef MRT_REF_TIMING_ONLY   // the timing-only build (reference's own flags incl. -fno-rtti, host libm) has no scene dump
 // ---------------------------------------------------------------- scene dump
 static void ind(FILE *f, int d) { for (int i = 0; i < d; i++) fputc(' ', f); }
 static void pv(FILE *f, const char *name, const Vec3 &v) {
@@ -213,6 +219,8 @@ static void dump_scene(FILE *f, const scene &sc) {
     }
 }
 
+#endif   // MRT_REF_TIMING_ONLY
+
 // ------------------------------------------------------------------- helpers
 static const char *argval(int argc, char **argv, const char *name, const char *def) {
     for (int i = 2; i + 1 < argc; i++) if (!strcmp(argv[i], name)) return argv[i + 1];
@@ -260,6 +268,12 @@ static int cmd_render(int argc, char **argv) {
     *getParams() = p;
 
     scene sc = build_scene(p.sceneSelect, W, H);
+    if (!strcmp(argval(argc, argv, "-lights", "ref"), "all") && sc.biased_objects) {
+        // The Cornell box and the final scene allocate a light list of TWO objects (ceiling light, glass sphere) but pass
+        // count 1 (scene.cpp:326-329, 456-459).  "-lights all" uses both, so that sphere::pdf_value / pdf_generate
+        // (sphere.cpp:63-79) and random_towards_sphere (pcg.cpp:125-133) -- dead code in all nine stock scenes -- run.
+        if (p.sceneSelect == 5 || p.sceneSelect == 7) ((object_list<scene_object> *) sc.biased_objects)->count = 2;
+    }
 
     // regular sample grid, main.cpp:319-332
     uint32 sq = (uint32) MRT::sqrt((float) spp);
@@ -336,11 +350,12 @@ static int cmd_render(int argc, char **argv) {
 
 // --------------------------------------------------------------------- stock
 static int cmd_stock(int argc, char **argv) {
-    const char *dump = nullptr;
+    const char *dump = nullptr, *dump_argb = nullptr;
     std::vector<char *> args;
     args.push_back(argv[0]);
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "-dump") && i + 1 < argc) { dump = argv[++i]; continue; }
+        if (!strcmp(argv[i], "-dumpargb") && i + 1 < argc) { dump_argb = argv[++i]; continue; }
         args.push_back(argv[i]);
     }
     MRT_headless_quiet = true;
@@ -361,6 +376,12 @@ static int cmd_stock(int argc, char **argv) {
            p->sceneSelect, p->bufferWidth, p->bufferHeight, sq * sq, p->maxBounces, p->numThreads,
            p->threadingMode, trace_s, wall, (unsigned long long) (size_t) G_rayCounter, paths,
            trace_s > 0 ? (size_t) G_rayCounter / trace_s * 1e-6 : 0.0, trace_s > 0 ? paths / trace_s * 1e-6 : 0.0);
+    if (dump_argb) {   // G_backBuffer: the reference's own tone map of its final frame (main.cpp:416-444), raw uint32 ARGB
+        FILE *f = fopen(dump_argb, "wb");
+        if (!f) { perror(dump_argb); return 1; }
+        fwrite(G_backBuffer, sizeof(uint32), (size_t) p->bufferWidth * p->bufferHeight, f);
+        fclose(f);
+    }
     if (dump) {
         uint32 W = p->bufferWidth, H = p->bufferHeight;
         std::vector<float> acc((size_t) W * H * 4);
@@ -380,6 +401,7 @@ static int cmd_stock(int argc, char **argv) {
     return 0;
 }
 
+#ifndef MRT_REF_TIMING_ONLY
 // ---------------------------------------------------------------- dump-scene
 static int cmd_dump_scene(int argc, char **argv) {
     uint32 W = strtoul(argval(argc, argv, "-width", "500"), 0, 0);
@@ -388,6 +410,8 @@ static int cmd_dump_scene(int argc, char **argv) {
     const char *out = argval(argc, argv, "-out", nullptr);
     MRT_headless_quiet = true;
     scene sc = build_scene(sel, W, H);
+    if (!strcmp(argval(argc, argv, "-lights", "ref"), "all") && sc.biased_objects && (sel == 5 || sel == 7))
+        ((object_list<scene_object> *) sc.biased_objects)->count = 2;   // see cmd_render
     FILE *f = out ? fopen(out, "w") : stdout;
     if (!f) { perror(out); return 1; }
     dump_scene(f, sc);
@@ -453,6 +477,8 @@ static int cmd_dump_image(int argc, char **argv) {
     return 0;
 }
 
+#endif   // MRT_REF_TIMING_ONLY
+
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: %s render|stock|dump-scene|kat|dump-image ...\n", argv[0]);
@@ -460,9 +486,11 @@ int main(int argc, char **argv) {
     }
     if (!strcmp(argv[1], "render")) return cmd_render(argc, argv);
     if (!strcmp(argv[1], "stock")) return cmd_stock(argc, argv);
+#ifndef MRT_REF_TIMING_ONLY
     if (!strcmp(argv[1], "dump-scene")) return cmd_dump_scene(argc, argv);
     if (!strcmp(argv[1], "kat")) return cmd_kat();
     if (!strcmp(argv[1], "dump-image")) return cmd_dump_image(argc, argv);
+#endif
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 2;
 }

@@ -26,6 +26,11 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, f"golden_scene{scene}.npz"), acc=acc, scene=scene, width=W, height=H,
                             spp=SPP, depth=DEPTH, seed=np.uint64(oracle_util.DEFAULT_SEED), rays=np.uint64(meta["rays"]))
         print("scene", scene, "rays", meta["rays"])
+    # light list with both allocated entries (`-lights all`): the sphere-light importance sampling path (sphere.cpp:63-79)
+    for scene in (5, 7):
+        acc, meta = oracle_util.ref_render(scene, W, H, 16, DEPTH, all_lights=True)
+        np.savez_compressed(os.path.join(HERE, f"golden_all_lights_scene{scene}.npz"), acc=acc, scene=scene, width=W, height=H,
+                            spp=16, depth=DEPTH, seed=np.uint64(oracle_util.DEFAULT_SEED), rays=np.uint64(meta["rays"]))
     kat = oracle_util.ref_run(["kat"]).stdout
     open(os.path.join(HERE, "kat.txt"), "w").write(kat)
     # scene dumps printed by the reference + matching renders, used to test oracle/mrt_oracle.c without the reference binary

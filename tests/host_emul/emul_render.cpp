@@ -12,10 +12,12 @@
 #include <thread>
 #include <vector>
 
+#define MRT_COUNT_OPS 1   // algorithmic operation counters (trace_core.h: MRT_OP) -- this test binary only
 #include "scene_graph.h"
 #include "trace_core.h"
 
 using namespace mrt;
+namespace mrt { thread_local OpCounts mrt_ops; }
 
 static const char *argval(int argc, char **argv, const char *name, const char *def) {
     for (int i = 1; i + 1 < argc; i++) if (!strcmp(argv[i], name)) return argv[i + 1];
@@ -79,6 +81,7 @@ int main(int argc, char **argv) {
     Counters total;
     memset(&total, 0, sizeof(total));
     std::vector<Counters> per_thread(nthreads);
+    std::vector<OpCounts> ops_thread(nthreads);
     auto worker = [&](uint32_t tid) {
         std::vector<uint32_t> stack_mem(d.stack_words + 8);
         Counters cnt;
@@ -114,6 +117,7 @@ int main(int argc, char **argv) {
             }
         }
         per_thread[tid] = cnt;
+        ops_thread[tid] = mrt_ops;
     };
     std::vector<std::thread> th;
     for (uint32_t i = 0; i < nthreads; i++) th.emplace_back(worker, i);
@@ -122,9 +126,20 @@ int main(int argc, char **argv) {
         total.rays += c.rays; total.aabb += c.aabb; total.sphere += c.sphere; total.rect += c.rect;
         total.tri += c.tri; total.vol += c.vol; total.xform += c.xform;
     }
+    OpCounts ops;
+    memset(&ops, 0, sizeof(ops));
+    for (auto &o : ops_thread) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&o);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&ops);
+        for (size_t i = 0; i < sizeof(OpCounts) / sizeof(unsigned long long); i++) dst[i] += src[i];
+    }
     printf("{\"mode\":\"emul\",\"scene\":%u,\"rays\":%llu,\"aabb\":%llu,\"sphere\":%llu,\"rect\":%llu,\"tri\":%llu,\"vol\":%llu,"
-           "\"xform\":%llu,\"stack_words\":%u}\n",
-           scene, total.rays, total.aabb, total.sphere, total.rect, total.tri, total.vol, total.xform, d.stack_words);
+           "\"xform\":%llu,\"stack_words\":%u,\"paths\":%llu,\"ray_ctor\":%llu,\"rng\":%llu,\"sphere_hit\":%llu,\"sphere_moving\":%llu,"
+           "\"rect_hit\":%llu,\"tri_hit\":%llu,\"translate\":%llu,\"rotate\":%llu,\"lambert\":%llu,\"metal\":%llu,\"dielectric\":%llu,"
+           "\"isotropic\":%llu,\"lightpdf\":%llu,\"perlin\":%llu,\"image\":%llu,\"checker\":%llu,\"sky\":%llu}\n",
+           scene, total.rays, total.aabb, total.sphere, total.rect, total.tri, total.vol, total.xform, d.stack_words, ops.paths, ops.ray_ctor, ops.rng,
+           ops.sphere_hit, ops.sphere_moving, ops.rect_hit, ops.tri_hit, ops.translate, ops.rotate, ops.lambert, ops.metal, ops.dielectric,
+           ops.isotropic, ops.lightpdf, ops.perlin, ops.image, ops.checker, ops.sky);
     if (out) {
         FileHeader h;
         memset(&h, 0, sizeof(h));

@@ -34,25 +34,25 @@ def ref_run(args, **kw):
     return subprocess.run([REF_BIN] + [str(a) for a in args], cwd=RUN_DIR, check=True, capture_output=True, text=True, **kw)
 
 
-def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0, crop=None):
+def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0, crop=None, all_lights=False):
     """Oracle render with per-(pixel, sample) RNG streams; returns (acc[h,w,4], meta). Cached in /tmp.
     crop = (x0, y0, x1, y1): only that window of the frame (stream ids and u,v stay the full frame's)."""
     from miniraytracer_b200.accfile import read_acc
     os.makedirs(CACHE, exist_ok=True)
     st = os.stat(REF_BIN)
-    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{crop}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
+    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{crop}-{all_lights}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
     path = os.path.join(CACHE, f"ref_{key}.bin")
     if not os.path.exists(path):
         tmp = path + f".{os.getpid()}.tmp"
         ref_run(["render", "-scene", scene, "-width", width, "-height", height, "-samples", spp, "-depth", depth,
                  "-seed", seed, "-s0", s0, "-s1", s1, "-threads", threads, "-out", tmp] +
-                (["-x0", crop[0], "-y0", crop[1], "-x1", crop[2], "-y1", crop[3]] if crop else []))
+                (["-x0", crop[0], "-y0", crop[1], "-x1", crop[2], "-y1", crop[3]] if crop else []) + (["-lights", "all"] if all_lights else []))
         os.replace(tmp, path)
     return read_acc(path)
 
 
-def ref_dump_scene(scene, width, height, out):
-    ref_run(["dump-scene", "-scene", scene, "-width", width, "-height", height, "-out", out])
+def ref_dump_scene(scene, width, height, out, all_lights=False):
+    ref_run(["dump-scene", "-scene", scene, "-width", width, "-height", height, "-out", out] + (["-lights", "all"] if all_lights else []))
 
 
 def build_emul():

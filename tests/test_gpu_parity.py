@@ -49,6 +49,26 @@ def test_golden_fixtures(scene):
 
 needs_ref = pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not on this box")
 
+
+@pytest.mark.parametrize("scene", [5, 7])
+def test_sphere_light_golden(scene):
+    """Light list {ceiling light, glass sphere} (MRT_SCENE_ALL_LIGHTS; oracle: `-lights all` = the reference's list with its count
+    set to the 2 entries it allocates, scene.cpp:326-329,456-459): sphere::pdf_value / pdf_generate (sphere.cpp:63-79) and
+    random_towards_sphere (pcg.cpp:125-133), dead code in the stock scenes, against the reference."""
+    g = np.load(os.path.join(GOLDEN, f"golden_all_lights_scene{scene}.npz"))
+    acc, st = _gpu_render(scene | api.SCENE_ALL_LIGHTS, int(g["width"]), int(g["height"]), int(g["spp"]), int(g["depth"]))
+    _check(acc, g["acc"], int(g["rays"]), st)
+    stock = np.load(os.path.join(GOLDEN, f"golden_scene{scene}.npz"))
+    assert int(g["rays"]) != int(stock["rays"]) * 4      # (the stock golden has 4 spp) the second light changes the paths
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 240, 135, 36), (7, 160, 90, 16)])
+def test_sphere_light_parity_vs_oracle(scene, w, h, spp):
+    ref, meta = oracle_util.ref_render(scene, w, h, spp, all_lights=True)
+    acc, st = _gpu_render(scene | api.SCENE_ALL_LIGHTS, w, h, spp)
+    _check(acc, ref, meta["rays"], st)
+
 # BASELINE.json configs: C1 exactly; C2..C5 at the config's scene/aspect/depth with the resolution and spp the
 # CPU oracle finishes in seconds (per-pixel parity needs identical streams, not convergence)
 CONFIGS = [
@@ -138,7 +158,7 @@ def test_finalize_matches_reference_accumulate():
     r.close(); hs.close()
     want = accfile.finalize(raw, 0.5)
     np.testing.assert_allclose(fin[..., :3], want, rtol=1e-6, atol=1e-7)
-    assert argb.shape == (h, w) and argb.max() > 0
+    assert argb.shape == (h, w) and argb.max() > 0      # values: test_tonemap_matches_reference
 
 
 def test_bad_arguments():
@@ -332,3 +352,36 @@ def test_cooperative_traversal_not_applicable():
     assert st["coop_trees"] == 0
     with pytest.raises(api.MrtError):
         _gpu_render(5, 64, 36, 16, tuning=dict(coop_trees=2))
+
+
+@pytest.mark.parametrize("scene", [5, 0, 7])
+def test_tonemap_matches_reference(scene):
+    """mrt_gpu_tonemap_device against the reference's own preview tone map (main.cpp:416-444 + ARGB32, vec3.h:327-333): the golden
+    pair is the reference's final linear frame and the ARGB buffer ITS main loop computed from it (tests/golden/make_golden_tonemap.py).
+    logf / log10f / powf differ by an ulp or two between the host libm and CUDA, so a channel may land on the other side of an
+    integer boundary: +-1 LSB per channel, and at least 99 % of the channels exactly equal."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, f"tonemap_scene{scene}.npz"))
+    lin, want = g["linear"], g["argb"]
+    h, w = want.shape
+    img = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda:0")
+    img[..., :3] = torch.from_numpy(lin).cuda()
+    img[..., 3] = 1.0
+    out = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+    hs = api.HostScene(5, w, h)
+    r = api.Renderer(hs, 0)
+    try:
+        r.set_stream(torch.cuda.current_stream().cuda_stream)
+        r.tonemap_device(img.data_ptr(), out.data_ptr(), w, h)
+        torch.cuda.synchronize()
+    finally:
+        r.close(); hs.close()
+    got = out.cpu().numpy().view(np.uint32)
+    assert (got >> 24).max() == 0 and (want >> 24).max() == 0
+    exact = 0
+    for shift in (16, 8, 0):
+        a, b = ((got >> shift) & 255).astype(np.int32), ((want >> shift) & 255).astype(np.int32)
+        assert np.abs(a - b).max() <= 1, (shift, np.abs(a - b).max())
+        exact += int((a == b).sum())
+    assert exact >= 0.99 * 3 * h * w, exact / (3 * h * w)
+    assert want.max() > 0

@@ -82,3 +82,20 @@ def test_core_crop_window_at_true_config_size(emul_bin, scene, w, h, spp, crop, 
     np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
     res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
     assert res["n_bad"] == 0, res
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 96, 54, 16), (7, 96, 54, 16)])
+def test_sphere_light_importance_sampling(emul_bin, scene, w, h, spp):
+    """sphere::pdf_value / pdf_generate (sphere.cpp:63-79) and random_towards_sphere (pcg.cpp:125-133) are dead in the nine stock
+    scenes: the Cornell box and the final scene allocate a light list {ceiling light, glass sphere} but pass count 1
+    (scene.cpp:326-329, 456-459).  With both entries (MRT_SCENE_ALL_LIGHTS here, `-lights all` in the oracle harness, which only
+    sets the list's count to the allocated 2) the sphere-light path runs on both sides and must agree like any other scene."""
+    ref, rmeta = oracle_util.ref_render(scene, w, h, spp, all_lights=True)
+    stock, smeta = oracle_util.ref_render(scene, w, h, spp)
+    assert rmeta["rays"] != smeta["rays"]            # the second light changes the paths
+    acc, meta = oracle_util.emul_render(emul_bin, scene | 0x100, w, h, spp)
+    assert meta["rays"] == rmeta["rays"]
+    np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
+    assert res["n_bad"] == 0, res

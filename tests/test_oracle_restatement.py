@@ -67,6 +67,18 @@ def test_restatement_crop_window_with_large_stream_ids(restatement, tmp_path):
     np.testing.assert_array_equal(acc, ref)
 
 
+@pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+@pytest.mark.parametrize("scene", [5, 7])
+def test_restatement_sphere_light(restatement, scene, tmp_path):
+    """Light list with both allocated entries (ceiling light + glass sphere): sphere pdf_value / pdf_generate, random_towards_sphere."""
+    dump = str(tmp_path / "scene.txt")
+    oracle_util.ref_dump_scene(scene, 96, 54, dump, all_lights=True)
+    ref, rmeta = oracle_util.ref_render(scene, 96, 54, 9, all_lights=True)
+    acc, meta = _run(restatement, dump, 96, 54, 9, 0)
+    assert meta["rays"] == rmeta["rays"]
+    np.testing.assert_array_equal(acc, ref)
+
+
 @pytest.mark.parametrize("scene", [2, 3, 5, 6])
 def test_restatement_on_committed_dumps(restatement, scene):
     """Runs without the reference binary: committed scene dumps (printed by the reference) + committed golden
