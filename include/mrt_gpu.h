@@ -162,6 +162,12 @@ int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host);
 /* The same tone map on device buffers: img_dev = width*height float4 (finalised linear image), argb_dev = width*height
  * uint32; asynchronous on the scene's stream. */
 int mrt_gpu_tonemap_device(MrtScene *s, const void *img_dev, void *argb_dev, uint32_t width, uint32_t height);
+/* Samples-per-pixel sharding inside one process: the n scenes rendered the same frame (same size) on n GPUs, each its own
+ * sample slice.  Sums the accumulators in scene order and applies mean + luminance clamp (main.cpp:168-173) in one kernel per
+ * GPU over peer memory (NVLink / NVSwitch: each GPU reduces a stripe of the pixels and stores it into scenes[0]'s image), then
+ * optionally tone-maps on scenes[0]'s GPU.  rgba_host (width*height*4 floats) and / or argb_host (width*height uint32) receive
+ * the result; either may be NULL.  Blocks.  Scenes on the same device work too (no peer access involved). */
+int mrt_gpu_reduce_finalize(MrtScene **scenes, int n, float max_luminance, float *rgba_host, uint32_t *argb_host);
 /* Requests the running render to stop early (G_isRunning = false, main.cpp:274). */
 int mrt_gpu_cancel(MrtScene *s);
 void mrt_gpu_destroy(MrtScene *s);

@@ -90,7 +90,7 @@ EXPORTS = [
     "mrt_last_error", "mrt_params_default", "mrt_params_parse", "mrt_scene_create", "mrt_scene_desc",
     "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_tuning", "mrt_gpu_set_stream",
     "mrt_gpu_bind_accumulator", "mrt_gpu_render_async", "mrt_gpu_poll", "mrt_gpu_wait", "mrt_gpu_stats",
-    "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_tonemap_device", "mrt_gpu_cancel", "mrt_gpu_destroy",
+    "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_tonemap_device", "mrt_gpu_reduce_finalize", "mrt_gpu_cancel", "mrt_gpu_destroy",
 ]
 
 
@@ -142,6 +142,7 @@ def load(build_if_missing=True):
     lib.mrt_gpu_readback.argtypes = [vp, vp, C.c_int]
     lib.mrt_gpu_tonemap.argtypes = [vp, vp]
     lib.mrt_gpu_tonemap_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32]
+    lib.mrt_gpu_reduce_finalize.argtypes = [C.POINTER(vp), C.c_int, C.c_float, vp, vp]
     lib.mrt_gpu_cancel.argtypes = [vp]
     lib.mrt_gpu_destroy.argtypes = [vp]
     lib.mrt_gpu_destroy.restype = None
@@ -309,6 +310,19 @@ class Renderer:
             self.close()
         except Exception:
             pass
+
+
+def reduce_finalize(renderers, max_luminance=1000.0, tonemap=False):
+    """mrt_gpu_reduce_finalize: sum the accumulators of renderers that rendered the same frame (one sample slice each, one GPU
+    each), finalise over NVLink peer memory; returns the finalised float image (and the ARGB tone map if asked)."""
+    lib = load()
+    w, h = renderers[0]._size
+    arr = (C.c_void_p * len(renderers))(*[r._h.value for r in renderers])
+    img = np.empty((h, w, 4), dtype=np.float32)
+    argb = np.empty((h, w), dtype=np.uint32) if tonemap else None
+    _check(lib.mrt_gpu_reduce_finalize(arr, len(renderers), C.c_float(max_luminance), img.ctypes.data_as(C.c_void_p),
+                                       argb.ctypes.data_as(C.c_void_p) if tonemap else None))
+    return (img, argb) if tonemap else img
 
 
 def render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, device=0, asset_dir=None, finalize=False, tuning=None, **kw):

@@ -4,8 +4,9 @@
 // preview of platform_linux.cpp is optional in the reference's design and SDL2
 // is not available here), so the "window title" statistics go to stdout and the
 // image goes to a file.  With -gpus N the samples per pixel are split across N
-// devices of this process and the accumulators are summed on the host (the
-// torch.distributed/NCCL path of bench.py is the multi-process equivalent).
+// devices of this process; the accumulators are summed, finalised and tone-mapped
+// on the GPUs over NVLink peer memory (mrt_gpu_reduce_finalize) -- the
+// torch.distributed/NCCL path of bench.py is the multi-process equivalent.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -132,49 +133,17 @@ int main(int argc, char **argv) {
            rays * 1e-6 / secs, secs * 1e6 / (double) rays, paths * 1e-6 / secs, kernel_ms, (unsigned long long) dropped);
 
     if (p.out_path[0]) {
-        std::vector<float> sum((size_t) W * H * 4, 0.0f), part((size_t) W * H * 4);
-        for (uint32_t g = 0; g < G; g++) {
-            mrt_gpu_init((int) g, nullptr);
-            if (mrt_gpu_readback(scenes[g], part.data(), 0)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
-            for (size_t i = 0; i < sum.size(); i++) sum[i] += part[i];
+        // Sum of the GPUs' accumulators + mean + luminance clamp (main.cpp:168-173) + tone map (main.cpp:416-444): one call,
+        // done on the GPUs over NVLink peer memory (mrt_gpu_reduce_finalize); the host only receives the finished image.
+        const size_t len = strlen(p.out_path);
+        const bool pfm = len > 4 && !strcmp(p.out_path + len - 4, ".pfm");
+        std::vector<float> rgba(pfm ? (size_t) W * H * 4 : 0);
+        std::vector<uint32_t> argb(pfm ? 0 : (size_t) W * H);
+        if (mrt_gpu_reduce_finalize(scenes.data(), (int) G, p.max_luminance, pfm ? rgba.data() : nullptr, pfm ? nullptr : argb.data())) {
+            fprintf(stderr, "error: %s\n", mrt_last_error());
+            return 1;
         }
-        // mean over finite samples + luminance clamp (main.cpp:168-173)
-        for (size_t i = 0; i < (size_t) W * H; i++) {
-            float *c = &sum[i * 4];
-            if (c[3] > 0) { c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3]; }
-            float lum = (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f;
-            if (lum > p.max_luminance) { float k = p.max_luminance / lum; c[0] *= k; c[1] *= k; c[2] *= k; }
-        }
-        size_t len = strlen(p.out_path);
-        int rc = 0;
-        if (len > 4 && !strcmp(p.out_path + len - 4, ".pfm")) {
-            rc = write_pfm(p.out_path, sum.data(), W, H);
-        } else if (G == 1) {
-            std::vector<uint32_t> argb((size_t) W * H);
-            mrt_gpu_init(0, nullptr);
-            if (mrt_gpu_tonemap(scenes[0], argb.data())) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
-            rc = write_ppm(p.out_path, argb.data(), W, H);
-        } else {
-            // host tone map of the combined image (main.cpp:416-444)
-            float L_wmax = 0;
-            for (size_t i = 0; i < (size_t) W * H; i++) {
-                const float *c = &sum[i * 4];
-                L_wmax = std::fmax(L_wmax, (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f);
-            }
-            float bias = logf(0.7f) / logf(0.5f), invlogmax = 1.0f / log10f(L_wmax + 1.0f), invmax = 1.0f / L_wmax;
-            std::vector<uint32_t> argb((size_t) W * H);
-            for (size_t i = 0; i < (size_t) W * H; i++) {
-                const float *c = &sum[i * 4];
-                float lum = (c[0] * 0.212655f + c[1] * 0.715158f) + c[2] * 0.072187f;
-                float lum_new = (230.0f * 0.01f * invlogmax) * (logf(lum + 1.0f) / logf(2 + powf(lum * invmax, bias) * 8));
-                float d = lum + 0.00001f;
-                uint32_t r = (uint32_t) (std::fmin(lum_new * c[0] / d, 1.0f) * 255.99f);
-                uint32_t g = (uint32_t) (std::fmin(lum_new * c[1] / d, 1.0f) * 255.99f);
-                uint32_t b = (uint32_t) (std::fmin(lum_new * c[2] / d, 1.0f) * 255.99f);
-                argb[i] = (r << 16) | (g << 8) | b;
-            }
-            rc = write_ppm(p.out_path, argb.data(), W, H);
-        }
+        const int rc = pfm ? write_pfm(p.out_path, rgba.data(), W, H) : write_ppm(p.out_path, argb.data(), W, H);
         if (rc) { fprintf(stderr, "cannot write %s\n", p.out_path); return 1; }
         printf("wrote %s\n", p.out_path);
     }

@@ -67,6 +67,37 @@ __global__ void tonemap_kernel(const float4 *img, uint32_t *argb, uint32_t n, co
     argb[i] = ((uint32_t) r << 16) | ((uint32_t) g << 8) | (uint32_t) b;   // ARGB32, vec3.h:327-333
 }
 
+// --------------------------------------------------------------- multi-GPU sum + finalize over NVLink
+// The path shards by samples per pixel: GPU k holds the accumulator (sum of finite radiance, count) of its sample slice for
+// the whole frame.  This kernel is the exchange step as ONE pass over peer memory: the launching GPU owns a stripe
+// of the pixels, reads that stripe from every GPU's accumulator (its own from HBM, the others' over NVLink / NVSwitch -- peer
+// loads), adds them in GPU order (deterministic, the order a host loop would use), applies mean + luminance clamp
+// (main.cpp:168-173) and stores the finished pixels straight into the root GPU's image (peer store).  Every byte crosses
+// NVLink once; nothing goes through the host.
+constexpr int kMaxReduceGpus = 16;
+struct ReduceArgs {
+    const float4 *acc[kMaxReduceGpus];
+    int n;
+};
+__global__ void reduce_finalize_kernel(const ReduceArgs a, float4 *out, uint32_t begin, uint32_t end, float max_lum) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    float4 s = a.acc[0][i];
+#pragma unroll 1
+    for (int k = 1; k < a.n; k++) {
+        const float4 v = a.acc[k][i];
+        s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
+    }
+    float r = 0, g = 0, b = 0;
+    if (s.w > 0) { r = __fdiv_rn(s.x, s.w); g = __fdiv_rn(s.y, s.w); b = __fdiv_rn(s.z, s.w); }
+    const float lum = __fadd_rn(__fadd_rn(__fmul_rn(r, 0.212655f), __fmul_rn(g, 0.715158f)), __fmul_rn(b, 0.072187f));
+    if (lum > max_lum) {
+        const float k = __fdiv_rn(max_lum, lum);
+        r = __fmul_rn(r, k); g = __fmul_rn(g, k); b = __fmul_rn(b, k);
+    }
+    out[i] = make_float4(r, g, b, s.w);
+}
+
 }  // namespace mrt
 
 // =========================================================================
@@ -736,6 +767,61 @@ extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(argb_host, s->argb_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MRT_OK;
+}
+
+// Samples-per-pixel sharding inside ONE process (the C++ host, main_host.cpp -gpus N): sum the accumulators of n scenes that
+// rendered the same frame on n GPUs, finalise, and leave the image on scenes[0]'s GPU -- see reduce_finalize_kernel.
+extern "C" int mrt_gpu_reduce_finalize(MrtScene **scenes, int n, float max_luminance, float *rgba_host, uint32_t *argb_host) {
+    if (!scenes || n < 1 || n > kMaxReduceGpus) { set_error("mrt_gpu_reduce_finalize: need 1..16 scenes"); return MRT_E_INVALID; }
+    for (int k = 0; k < n; k++) {
+        if (!scenes[k] || !scenes[k]->rendered) { set_error("mrt_gpu_reduce_finalize: every scene must have rendered"); return MRT_E_STATE; }
+        if (scenes[k]->last_w != scenes[0]->last_w || scenes[k]->last_h != scenes[0]->last_h) { set_error("mrt_gpu_reduce_finalize: frame sizes differ"); return MRT_E_INVALID; }
+    }
+    MrtScene *root = scenes[0];
+    const uint32_t W = root->last_w, H = root->last_h, P = W * H;
+    // peer access between every pair of distinct devices (NVLink / NVSwitch on a B200 node)
+    for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) {
+            const int da = scenes[a]->device, db = scenes[b]->device;
+            if (da == db) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, da, db));
+            if (!can) { set_error("mrt_gpu_reduce_finalize: no peer access between the GPUs (NVLink / P2P required)"); return MRT_E_CUDA; }
+            CUDA_TRY(cudaSetDevice(da));
+            cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return MRT_E_CUDA; }
+        }
+    CUDA_TRY(cudaSetDevice(root->device));
+    int rc = ensure_final(root, P);
+    if (rc) return rc;
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.n = n;
+    for (int k = 0; k < n; k++) ra.acc[k] = scenes[k]->last_acc;
+    std::vector<cudaEvent_t> done(n, nullptr);
+    auto cleanup = [&]() { for (cudaEvent_t e : done) if (e) cudaEventDestroy(e); };
+    for (int g = 0; g < n; g++) {
+        MrtScene *sg = scenes[g];
+        const uint32_t begin = (uint32_t) ((uint64_t) P * g / n), end = (uint32_t) ((uint64_t) P * (g + 1) / n);
+        if (cudaSetDevice(sg->device) != cudaSuccess) { cleanup(); set_error("cudaSetDevice"); return MRT_E_CUDA; }
+        for (int k = 0; k < n; k++)   // the stripe kernel reads every accumulator: wait for every render
+            if (cudaStreamWaitEvent(sg->stream, scenes[k]->ev1, 0) != cudaSuccess) { cleanup(); set_error("cudaStreamWaitEvent"); return MRT_E_CUDA; }
+        if (end > begin) reduce_finalize_kernel<<<(end - begin + 255) / 256, 256, 0, sg->stream>>>(ra, root->final_buf, begin, end, max_luminance);
+        if (cudaGetLastError() != cudaSuccess || cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(done[g], sg->stream) != cudaSuccess) { cleanup(); set_error("mrt_gpu_reduce_finalize: launch failed"); return MRT_E_CUDA; }
+    }
+    CUDA_TRY(cudaSetDevice(root->device));
+    for (int g = 0; g < n; g++) CUDA_TRY(cudaStreamWaitEvent(root->stream, done[g], 0));
+    if (argb_host) {
+        rc = mrt_gpu_tonemap_device(root, root->final_buf, root->argb_buf, W, H);
+        if (rc) { cleanup(); return rc; }
+        CUDA_TRY(cudaMemcpyAsync(argb_host, root->argb_buf, (size_t) P * sizeof(uint32_t), cudaMemcpyDeviceToHost, root->stream));
+    }
+    if (rgba_host) CUDA_TRY(cudaMemcpyAsync(rgba_host, root->final_buf, (size_t) P * sizeof(float4), cudaMemcpyDeviceToHost, root->stream));
+    CUDA_TRY(cudaStreamSynchronize(root->stream));
+    cleanup();
     return MRT_OK;
 }
 

@@ -385,3 +385,42 @@ def test_tonemap_matches_reference(scene):
         exact += int((a == b).sum())
     assert exact >= 0.99 * 3 * h * w, exact / (3 * h * w)
     assert want.max() > 0
+
+
+@pytest.mark.parametrize("devices", [(0, 0, 0), (0, 1)])
+def test_reduce_finalize_over_peer_memory(devices):
+    """mrt_gpu_reduce_finalize: n scenes that rendered disjoint sample slices of the same frame are summed in scene order,
+    finalised (mean + luminance clamp) and tone-mapped on the GPUs.  (0, 0, 0): three scenes on one device (always runs);
+    (0, 1): two GPUs, the stripes cross NVLink as peer loads / stores (needs gpurun --gpus 2)."""
+    import torch
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip("needs %d GPUs" % (max(devices) + 1))
+    w, h, spp = 160, 90, 36
+    n = len(devices)
+    hs = api.HostScene(7, w, h)
+    rs = [api.Renderer(hs, d) for d in devices]
+    try:
+        parts = []
+        for k, r in enumerate(rs):
+            r.render_async(w, h, spp, sample_begin=spp * k // n, sample_end=spp * (k + 1) // n, max_luminance=2.0)
+        for r in rs:
+            parts.append(r.readback())
+        img, argb = api.reduce_finalize(rs, max_luminance=2.0, tonemap=True)
+        one = api.Renderer(hs, devices[0])
+        one.render_async(w, h, spp, max_luminance=2.0)
+        full = one.readback()
+        argb_one = one.tonemap()
+        one.close()
+    finally:
+        for r in rs:
+            r.close()
+        hs.close()
+    acc = parts[0].copy()
+    for p in parts[1:]:
+        acc += p                                   # scene order, float32: what the kernel does
+    np.testing.assert_array_equal(img[..., 3], full[..., 3])
+    np.testing.assert_allclose(img[..., :3], accfile.finalize(acc, 2.0), rtol=1e-6, atol=1e-7)
+    res = accfile.compare(img[..., :3], accfile.finalize(full, 2.0), rel=1e-5)
+    assert res["n_bad"] == 0, res
+    d = np.abs(((argb >> 8) & 255).astype(np.int32) - ((argb_one >> 8) & 255).astype(np.int32))
+    assert d.max() <= 1
