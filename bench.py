@@ -237,20 +237,48 @@ class Workload:
         self.r.finalize_device(self.acc.data_ptr(), self.final.data_ptr(), self.W, self.H)
 
     def step_e2e(self):
-        """Through the C ABI with HOST buffers: scene tables H2D (mrt_gpu_scene_upload) + render + reduce + finalize + frame D2H."""
+        """Through the C ABI with HOST buffers: scene tables H2D (mrt_gpu_scene_upload) + render + reduce + finalize + frame D2H.
+        Frames are double-buffered: the D2H of frame k runs on a copy stream while the host uploads frame k+1 and the GPU starts
+        rendering it; a frame is retired (its copy awaited, its scene handle closed) one step later."""
         import torch.distributed as dist
         torch, api = self.torch, self.api
+        if not hasattr(self, "_inflight"):
+            self._inflight, self._frame = [], 0
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._final2 = [self.final, torch.empty_like(self.final)]
+            self._host2 = [self.host_out, torch.empty((self.H, self.W, 4), dtype=torch.float32, pin_memory=True)]
+        k = self._frame & 1
         r2 = api.Renderer(self.hs, self.local_rank)
         r2.set_stream(self.stream.cuda_stream)
         r2.bind_accumulator(self.acc.data_ptr(), self.W, self.H)
         r2.render_async(self.W, self.H, self.spp, self.depth, sample_begin=self.s_begin, sample_end=self.s_end)
         if self.world > 1:
             dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        done = torch.cuda.Event()
         if self.rank == 0:
-            r2.finalize_device(self.acc.data_ptr(), self.final.data_ptr(), self.W, self.H)
-            self.host_out.copy_(self.final, non_blocking=True)
-        torch.cuda.synchronize()
-        r2.close()
+            r2.finalize_device(self.acc.data_ptr(), self._final2[k].data_ptr(), self.W, self.H)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                self._host2[k].copy_(self._final2[k], non_blocking=True)
+                done.record(self._copy_stream)
+        else:
+            done.record(self.stream)
+        self._inflight.append((r2, done))
+        self._frame += 1
+        while len(self._inflight) > 1:
+            self._retire()
+
+    def _retire(self):
+        r, done = self._inflight.pop(0)
+        done.synchronize()
+        r.close()
+
+    def drain_e2e(self):
+        while getattr(self, "_inflight", []):
+            self._retire()
+        self.host_out = self._host2[(self._frame - 1) & 1] if getattr(self, "_frame", 0) else self.host_out
 
     def close(self):
         self.r.close()
@@ -340,11 +368,13 @@ def main():
             c = coop[-1]
             res["coop_trees"] = {"node_step_fill": c[1] / max(1.0, 32.0 * c[2]), "leaf_step_fill": c[3] / max(1.0, 32.0 * c[4])}
         if e2e_steps:
-            wl.step_e2e()                        # warm (pool / pinned buffers are cached per process)
+            wl.step_e2e()                        # warm (device buffers / pinned words / streams are cached per process)
+            wl.drain_e2e()
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
                 wl.step_e2e()
+            wl.drain_e2e()                       # every frame's D2H has landed in pinned host memory
             barrier()
             e2e_s = reduce_max(time.perf_counter() - t0)
             res["e2e"] = {"value": wl.paths_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes(wl.hs.desc),

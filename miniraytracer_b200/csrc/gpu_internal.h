@@ -25,7 +25,8 @@ constexpr int kBlock = 128;
 struct MrtScene {
     int device = 0;
     int sm_count = 0;
-    std::vector<void *> allocs;
+    void *scene_base = nullptr;   // the packed scene tables + control block (one cached device buffer)
+    size_t scene_bytes = 0, own_acc_bytes = 0, order_bytes = 0, final_bytes = 0, argb_bytes = 0;
     mrt::SceneView view;
     uint32_t stack_words = 0, stack_words_coop = 0;
     MrtTuning tuning = {};        // mrt_gpu_set_tuning; all zero = measured defaults

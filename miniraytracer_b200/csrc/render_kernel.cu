@@ -142,31 +142,68 @@ static bool pinned_slot_release(void *p) {
     return true;
 }
 
-// Path-pool buffers of mode B (tens of MB) are kept in a per-process cache when a scene is destroyed, so that
-// rendering a sequence of scenes / frames does not pay cudaMalloc + cudaFree (an implicit device sync) each time.
-struct PoolBuf { int device; uint32_t *ptr; size_t words; };
-static std::mutex g_pool_mu;
-static std::vector<PoolBuf> g_pool_free;
-static uint32_t *pool_acquire(int device, size_t words, size_t *got_words) {
+// Device buffers (scene tables, accumulators, path pool, sample staging, ...), the poll stream and the timing events of a
+// scene come from per-process caches and go back there when the scene is destroyed: a sequence of scenes / frames then pays
+// neither cudaMalloc nor cudaFree (an implicit device-wide sync that was measured at 0.2 .. 60 ms per call, and made the
+// end-to-end figure jitter by 10 %).  A request is served by a cached buffer of the same device whose capacity is between
+// the request and twice the request (so a 1 KB table never pins the 230 MB staging array); at most 32 buffers / 2 GiB stay cached.
+struct DevBuf { int device; void *ptr; size_t bytes; };
+static std::mutex g_buf_mu;
+static std::vector<DevBuf> g_buf_free;
+static size_t g_buf_cached = 0;
+static void *devbuf_acquire(int device, size_t bytes, size_t *got_bytes) {
+    if (bytes < 256) bytes = 256;
     {
-        std::lock_guard<std::mutex> lk(g_pool_mu);
-        for (size_t i = 0; i < g_pool_free.size(); i++)
-            if (g_pool_free[i].device == device && g_pool_free[i].words >= words) {
-                PoolBuf b = g_pool_free[i];
-                g_pool_free.erase(g_pool_free.begin() + i);
-                *got_words = b.words;
-                return b.ptr;
-            }
+        std::lock_guard<std::mutex> lk(g_buf_mu);
+        size_t best = g_buf_free.size();
+        for (size_t i = 0; i < g_buf_free.size(); i++)
+            if (g_buf_free[i].device == device && g_buf_free[i].bytes >= bytes && g_buf_free[i].bytes <= 2 * bytes &&
+                (best == g_buf_free.size() || g_buf_free[i].bytes < g_buf_free[best].bytes)) best = i;
+        if (best != g_buf_free.size()) {
+            DevBuf b = g_buf_free[best];
+            g_buf_free.erase(g_buf_free.begin() + best);
+            g_buf_cached -= b.bytes;
+            if (got_bytes) *got_bytes = b.bytes;
+            return b.ptr;
+        }
     }
-    uint32_t *p = nullptr;
-    if (cudaMalloc(&p, words * sizeof(uint32_t)) != cudaSuccess) return nullptr;
-    *got_words = words;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    if (got_bytes) *got_bytes = bytes;
     return p;
 }
-static void pool_release(int device, uint32_t *ptr, size_t words) {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool_free.size() >= 16) { cudaFree(ptr); return; }
-    g_pool_free.push_back(PoolBuf{device, ptr, words});
+static void devbuf_release(int device, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    if (g_buf_free.size() >= 32 || g_buf_cached + bytes > ((size_t) 2 << 30)) { cudaFree(ptr); return; }
+    g_buf_free.push_back(DevBuf{device, ptr, bytes});
+    g_buf_cached += bytes;
+}
+static uint32_t *pool_acquire(int device, size_t words, size_t *got_words) {
+    size_t got = 0;
+    uint32_t *p = (uint32_t *) devbuf_acquire(device, words * sizeof(uint32_t), &got);
+    *got_words = got / sizeof(uint32_t);
+    return p;
+}
+static void pool_release(int device, uint32_t *ptr, size_t words) { devbuf_release(device, ptr, words * sizeof(uint32_t)); }
+
+struct SyncObjs { int device; cudaStream_t stream; cudaEvent_t ev0, ev1; };
+static std::vector<SyncObjs> g_sync_free;
+static bool syncobjs_acquire(int device, SyncObjs *out) {
+    {
+        std::lock_guard<std::mutex> lk(g_buf_mu);
+        for (size_t i = 0; i < g_sync_free.size(); i++)
+            if (g_sync_free[i].device == device) { *out = g_sync_free[i]; g_sync_free.erase(g_sync_free.begin() + i); return true; }
+    }
+    out->device = device; out->stream = nullptr; out->ev0 = out->ev1 = nullptr;
+    if (cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&out->ev0) != cudaSuccess ||
+        cudaEventCreate(&out->ev1) != cudaSuccess) return false;
+    return true;
+}
+static void syncobjs_release(const SyncObjs &o) {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    if (g_sync_free.size() >= 32) { if (o.stream) cudaStreamDestroy(o.stream); if (o.ev0) cudaEventDestroy(o.ev0); if (o.ev1) cudaEventDestroy(o.ev1); return; }
+    g_sync_free.push_back(o);
 }
 
 extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
@@ -207,18 +244,17 @@ extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
 extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->rendered) cudaStreamSynchronize(s->stream);
-    for (void *p : s->allocs) cudaFree(p);
-    if (s->own_acc) cudaFree(s->own_acc);
-    if (s->order_dev) cudaFree(s->order_dev);
+    if (s->rendered) cudaEventSynchronize(s->ev1);   // this scene's own last render (not whatever else was queued on the stream since)
+    if (s->poll_stream) cudaStreamSynchronize(s->poll_stream);
+    if (s->scene_base) devbuf_release(s->device, s->scene_base, s->scene_bytes);
+    if (s->own_acc) devbuf_release(s->device, s->own_acc, s->own_acc_bytes);
+    if (s->order_dev) devbuf_release(s->device, s->order_dev, s->order_bytes);
     if (s->pool_dev) pool_release(s->device, s->pool_dev, s->pool_words);
     if (s->stage_dev) pool_release(s->device, s->stage_dev, s->stage_words);
-    if (s->final_buf) cudaFree(s->final_buf);
-    if (s->argb_buf) cudaFree(s->argb_buf);
+    if (s->final_buf) devbuf_release(s->device, s->final_buf, s->final_bytes);
+    if (s->argb_buf) devbuf_release(s->device, s->argb_buf, s->argb_bytes);
     if (s->poll_host && !pinned_slot_release(s->poll_host)) cudaFreeHost(s->poll_host);   // control words live in the scene allocation
-    if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->poll_stream || s->ev0 || s->ev1) syncobjs_release(SyncObjs{s->device, s->poll_stream, s->ev0, s->ev1});
     delete s;
 }
 
@@ -354,9 +390,9 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     {
         std::vector<unsigned char> staging(pk.total, 0);
         for (const Packer::Item &it : pk.items) memcpy(staging.data() + it.offset, it.host, it.bytes);
-        unsigned char *base = nullptr;
-        if (cudaMalloc((void **) &base, pk.total) != cudaSuccess) { set_error(std::string("cudaMalloc scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
-        s->allocs.push_back(base);
+        unsigned char *base = (unsigned char *) devbuf_acquire(s->device, pk.total, &s->scene_bytes);
+        if (!base) { set_error(std::string("cudaMalloc scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
+        s->scene_base = base;
         if (cudaMemcpy(base, staging.data(), pk.total, cudaMemcpyHostToDevice) != cudaSuccess) { set_error(std::string("cudaMemcpy scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
         for (const Packer::Item &it : pk.items) *it.dev = base + it.offset;
         s->counters = (unsigned long long *) (base + ctrl_off);          // 8 x 8 bytes
@@ -388,9 +424,12 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
         s->poll_host = (unsigned long long *) slot;
         s->cancel_pinned = (int *) ((unsigned char *) slot + 32);
     }
-    if (!cu(cudaStreamCreateWithFlags(&s->poll_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(MRT_E_CUDA);
-    if (!cu(cudaEventCreate(&s->ev0), "cudaEventCreate")) return fail(MRT_E_CUDA);
-    if (!cu(cudaEventCreate(&s->ev1), "cudaEventCreate")) return fail(MRT_E_CUDA);
+    {
+        SyncObjs so;
+        const bool ok = syncobjs_acquire(s->device, &so);
+        s->poll_stream = so.stream; s->ev0 = so.ev0; s->ev1 = so.ev1;
+        if (!ok) { cu(cudaGetLastError(), "cudaStreamCreate / cudaEventCreate"); set_error("cudaStreamCreate / cudaEventCreate failed"); return fail(MRT_E_CUDA); }
+    }
     *out = s;
     return MRT_OK;
 }
@@ -429,7 +468,7 @@ extern "C" int mrt_gpu_bind_accumulator(MrtScene *s, void *device_ptr, uint32_t 
 // work_queue.cpp:84-127, to spread the threads; on a GPU locality wins).
 static int ensure_order(MrtScene *s, uint32_t w, uint32_t h) {
     if (s->order_dev && s->order_w == w && s->order_h == h) return MRT_OK;
-    if (s->order_dev) { cudaFree(s->order_dev); s->order_dev = nullptr; }
+    if (s->order_dev) { CUDA_TRY(cudaStreamSynchronize(s->stream)); devbuf_release(s->device, s->order_dev, s->order_bytes); s->order_dev = nullptr; }
     std::vector<uint32_t> order;
     order.reserve((size_t) w * h);
     uint32_t side = 1;
@@ -447,7 +486,8 @@ static int ensure_order(MrtScene *s, uint32_t w, uint32_t h) {
         uint32_t x = compact(d), y = compact(d >> 1);
         if (x < w && y < h) order.push_back(y * w + x);
     }
-    CUDA_TRY(cudaMalloc(&s->order_dev, order.size() * sizeof(uint32_t)));
+    s->order_dev = (uint32_t *) devbuf_acquire(s->device, order.size() * sizeof(uint32_t), &s->order_bytes);
+    if (!s->order_dev) { set_error("cudaMalloc pixel order"); return MRT_E_CUDA; }
     CUDA_TRY(cudaMemcpy(s->order_dev, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     s->order_w = w;
     s->order_h = h;
@@ -480,8 +520,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         acc = s->ext_acc;
     } else {
         if (s->own_acc_pixels != n_pixels) {
-            if (s->own_acc) { cudaFree(s->own_acc); s->own_acc = nullptr; s->own_acc_pixels = 0; }
-            CUDA_TRY(cudaMalloc(&s->own_acc, (size_t) n_pixels * sizeof(float4)));
+            if (s->own_acc) { CUDA_TRY(cudaStreamSynchronize(s->stream)); devbuf_release(s->device, s->own_acc, s->own_acc_bytes); s->own_acc = nullptr; s->own_acc_pixels = 0; }
+            s->own_acc = (float4 *) devbuf_acquire(s->device, (size_t) n_pixels * sizeof(float4), &s->own_acc_bytes);
+            if (!s->own_acc) { set_error(std::string("cudaMalloc accumulator: ") + cudaGetErrorString(cudaGetLastError())); return MRT_E_CUDA; }
             s->own_acc_pixels = n_pixels;
             CUDA_TRY(cudaMemsetAsync(s->own_acc, 0, (size_t) n_pixels * sizeof(float4), s->stream));
         }
@@ -567,11 +608,14 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     };
     if (binned) {
         // chunk = warp task: ~4096 paths whatever the samples per pixel (the sums live in a staging array in global
-        // memory, not in shared memory), but at least 32 tasks per resident warp on small frames, at least 256 paths
+        // memory, not in shared memory), but at least 10 / 32 tasks per resident warp on small frames, at least 256 paths
         int rc = occupancy(0);
         if (rc) return rc;
         const uint64_t total = (uint64_t) n_pixels * ns;
-        uint64_t target = total / ((uint64_t) resident_warps * 32u);   // >= 32 tasks per resident warp: load balance at the end of the launch
+        // >= 10 big tasks per resident warp for list scenes (chunks cost about the same; the end of the launch is balanced by the
+        // small last chunks, below), >= 32 for scenes with trees, whose chunks differ several-fold in cost (mesh vs background
+        // pixels: measured 176 -> 249 ms on a 960x540x256 frame of scene 7 with 10)
+        uint64_t target = total / ((uint64_t) resident_warps * (s->has_trees ? 32u : 10u));
         if (target > 4096u) target = 4096u;
         if (target < 256u) target = 256u;
         K = (uint32_t) (target / ns);
@@ -606,6 +650,23 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.stack_words = stack_words;
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
+    if (binned) {
+        // Guided self-scheduling: big chunks first, the last stretch of the frame -- about two big chunks per resident warp --
+        // in chunks of a quarter and then a sixteenth of that size, so that at the end of the launch a warp waits for a
+        // small chunk, not a big one (with 18 big chunks per warp, the 1/8 slice of an 8-GPU run, the idle end was 3-5 %
+        // of the launch; profiles/r2_notes.md).  MrtTuning.chunk_pixels = uniform chunks of that size.
+        uint32_t k1 = K / 4u ? K / 4u : 1u, k2 = K / 16u ? K / 16u : 1u;
+        uint64_t tail = tn.chunk_pixels ? 0u : (uint64_t) 2u * resident_warps * K;     // pixels handed out in small chunks
+        if (tail > n_pixels / 4u) tail = n_pixels / 4u;
+        if (k1 == K) tail = 0;
+        const uint32_t p1 = n_pixels - (uint32_t) tail;                                 // run 0: [0, p1) in chunks of K
+        const uint32_t p2 = (k2 == k1) ? n_pixels : p1 + (uint32_t) (tail * 2u / 3u);   // run 1: [p1, p2) in chunks of k1; run 2: the rest
+        const uint32_t t1 = (p1 + K - 1u) / K, t2 = t1 + (p2 - p1 + k1 - 1u) / k1;
+        a.sched_task0[0] = 0; a.sched_task0[1] = t1; a.sched_task0[2] = t2;
+        a.sched_pix0[0] = 0; a.sched_pix0[1] = p1; a.sched_pix0[2] = p2; a.sched_pix0[3] = n_pixels;
+        a.sched_k[0] = K; a.sched_k[1] = k1; a.sched_k[2] = k2;
+        a.n_tasks = t2 + (n_pixels - p2 + k2 - 1u) / k2;
+    }
     uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
     const uint32_t blocks_needed = (a.n_tasks + warps_per_block - 1) / warps_per_block;
     if (grid > blocks_needed) grid = blocks_needed;
@@ -715,11 +776,13 @@ extern "C" int mrt_gpu_finalize_device(MrtScene *s, const void *acc_dev, void *o
 
 static int ensure_final(MrtScene *s, size_t n) {
     if (s->final_pixels != n) {
-        if (s->final_buf) { cudaFree(s->final_buf); s->final_buf = nullptr; }
-        if (s->argb_buf) { cudaFree(s->argb_buf); s->argb_buf = nullptr; }
+        if (s->final_buf || s->argb_buf) CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->final_buf) { devbuf_release(s->device, s->final_buf, s->final_bytes); s->final_buf = nullptr; }
+        if (s->argb_buf) { devbuf_release(s->device, s->argb_buf, s->argb_bytes); s->argb_buf = nullptr; }
         s->final_pixels = 0;
-        CUDA_TRY(cudaMalloc(&s->final_buf, n * sizeof(float4)));
-        CUDA_TRY(cudaMalloc(&s->argb_buf, n * sizeof(uint32_t)));
+        s->final_buf = (float4 *) devbuf_acquire(s->device, n * sizeof(float4), &s->final_bytes);
+        s->argb_buf = (uint32_t *) devbuf_acquire(s->device, n * sizeof(uint32_t), &s->argb_bytes);
+        if (!s->final_buf || !s->argb_buf) { set_error(std::string("cudaMalloc image buffers: ") + cudaGetErrorString(cudaGetLastError())); return MRT_E_CUDA; }
         s->final_pixels = n;
     }
     return MRT_OK;

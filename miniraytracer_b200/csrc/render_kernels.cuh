@@ -32,6 +32,10 @@ struct RenderArgs {
     uint32_t accumulate;
     uint32_t stack_words;
     uint32_t n_tasks, pixels_per_task;
+    // mode B, guided self-scheduling: the ticket queue hands out the frame in three runs of tasks with decreasing chunk size
+    // (pixels_per_task = the largest): run r starts at task sched_task0[r] / pixel sched_pix0[r] and uses chunks of sched_k[r]
+    // pixels; sched_pix0[3] = n_pixels.  Small last chunks keep the warps from idling while the last big chunk finishes.
+    uint32_t sched_task0[3], sched_pix0[4], sched_k[3];
     float4 *acc;
     unsigned int *ticket;             // global task counter
     unsigned long long *counters;     // [0] rays [1] warp iterations [2] nonfinite [4..7] cooperative traversal: node steps, node items, leaf steps, leaf items
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     st.base = smem_stack + (size_t) warp * a.stack_words * 32u + lane;
     st.stride = 32u;
     st.sp = 0;
-    const uint32_t K = a.pixels_per_task, NB = a.n_bins;
+    const uint32_t NB = a.n_bins;
     uint8_t *binq = reinterpret_cast<uint8_t *>(smem_stack + (size_t) kWarpsPerBlock * a.stack_words * 32u) + (size_t) warp * (NB + 1u) * kPoolCap;
     uint8_t *freeq = binq + (size_t) NB * kPoolCap;
     CoopArea ca;
@@ -354,8 +358,13 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         if (lane == 0) task = (*a.cancel) ? 0xFFFFFFFFu : atomicAdd(a.ticket, 1u);
         task = __shfl_sync(0xFFFFFFFFu, task, 0);
         if (task >= a.n_tasks) break;
-        const uint32_t pix0 = task * K;
-        const uint32_t kp = min(K, n_pixels - pix0);   // pixels in this chunk
+        const bool r1 = task >= a.sched_task0[1], r2 = task >= a.sched_task0[2];
+        const uint32_t run_task0 = r2 ? a.sched_task0[2] : (r1 ? a.sched_task0[1] : 0u);
+        const uint32_t run_pix0 = r2 ? a.sched_pix0[2] : (r1 ? a.sched_pix0[1] : 0u);
+        const uint32_t run_end = r2 ? a.sched_pix0[3] : (r1 ? a.sched_pix0[2] : a.sched_pix0[1]);
+        const uint32_t run_k = r2 ? a.sched_k[2] : (r1 ? a.sched_k[1] : a.sched_k[0]);
+        const uint32_t pix0 = run_pix0 + (task - run_task0) * run_k;
+        const uint32_t kp = min(run_k, run_end - pix0);   // pixels in this chunk
         const uint32_t n_items = kp * ns;
 #pragma unroll 1
         for (uint32_t i = lane; i < kPoolCap; i += 32u) freeq[i] = (uint8_t) i;

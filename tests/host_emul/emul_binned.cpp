@@ -86,6 +86,17 @@ int main(int argc, char **argv) {
     if (g_mode == 'P') K = chunk ? ((chunk + 31u) & ~31u) : 32u;
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
+    {   // guided schedule of the ticket queue (see mrt_gpu_render_async): -tail P = the last P pixels in chunks of K/4 and K/16
+        uint32_t tail = strtoul(argval(argc, argv, "-tail", "0"), 0, 0);
+        if (tail > n_pixels) tail = n_pixels;
+        const uint32_t k1 = K / 4u ? K / 4u : 1u, k2 = K / 16u ? K / 16u : 1u;
+        const uint32_t p1 = n_pixels - tail, p2 = p1 + tail * 2u / 3u;
+        const uint32_t t1 = (p1 + K - 1u) / K, t2 = t1 + (p2 - p1 + k1 - 1u) / k1;
+        a.sched_task0[0] = 0; a.sched_task0[1] = t1; a.sched_task0[2] = t2;
+        a.sched_pix0[0] = 0; a.sched_pix0[1] = p1; a.sched_pix0[2] = p2; a.sched_pix0[3] = n_pixels;
+        a.sched_k[0] = K; a.sched_k[1] = k1; a.sched_k[2] = k2;
+        if (g_mode == 'B') a.n_tasks = t2 + (n_pixels - p2 + k2 - 1u) / k2;
+    }
     // bins: classifier boxes are a grouping heuristic, any box will do -- the first rotate_y's bounds if the scene has one
     a.n_cls_boxes = 0; a.cls_pending = 0;
     if (bins >= 2 && d.n_rot) {

@@ -88,3 +88,14 @@ def test_cooperative_tree_traversal_matches_oracle_and_per_lane(emul_kernel_bin,
     assert meta["info"]["coop_node_steps"] > 0 and meta["info"]["coop_leaf_steps"] > 0 and meta0["info"]["coop_node_steps"] == 0
     np.testing.assert_array_equal(coop, lane)
     _same(coop, ref, meta["rays"], rmeta["rays"])
+
+
+@needs_ref
+def test_mode_b_guided_schedule_does_not_change_a_bit(emul_kernel_bin):
+    """Guided self-scheduling (big chunks first, the last pixels in chunks of a quarter / a sixteenth of the size) only changes
+    which warp task a pixel belongs to; samples are summed per pixel in item order, so the accumulator is bit-identical."""
+    base, m0 = oracle_util.emul_binned(emul_kernel_bin, 6, 20, 11, 16, chunk=16)
+    for tail in (37, 220):
+        acc, m = oracle_util.emul_binned(emul_kernel_bin, 6, 20, 11, 16, chunk=16, extra=["-tail", str(tail)])
+        assert m["info"]["tasks"] > m0["info"]["tasks"]
+        np.testing.assert_array_equal(acc, base)
