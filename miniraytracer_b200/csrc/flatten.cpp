@@ -371,6 +371,123 @@ bool coop_trees_supported(const MrtSceneDesc &d) {
     return d.n_bvh > 0;
 }
 
+// Structural check of a flattened scene that did not come straight out of flatten_scene (a scene file, a description built by
+// a caller of the C ABI): every typed reference and index inside its table, every child run terminated, Perlin tables of the
+// sizes the kernels read, image extents inside the image table, no reference cycles, and a traversal stack at least as deep
+// as the scene needs.  On success *stack_words_needed (may be null) is the depth the flattener would have computed.
+bool validate_scene_desc(const MrtSceneDesc &d, std::string *err, uint32_t *stack_words_needed) {
+    auto u = [](float f) { uint32_t v; memcpy(&v, &f, 4); return v; };
+    auto fail = [&](const char *what) { if (err) *err = what; return false; };
+    if ((d.n_sphere && !d.sphere) || (d.n_rect && !d.rect) || (d.n_list && !d.list) || (d.n_child && !d.child) || (d.n_bvh && !d.bvh) ||
+        (d.n_node2 && !d.node2) || (d.n_trileaf && !d.trileaf) || (d.n_tri && (!d.tri || !d.trin)) || (d.n_xlate && !d.xlate) ||
+        (d.n_rot && !d.rot) || (d.n_vol && !d.vol) || (d.n_mat && !d.mat) || (d.n_tex && !d.tex) || (d.n_lights && !d.lights) ||
+        (d.n_image_bytes && !d.image))
+        return fail("a table pointer is null although its count is not");
+    auto ref_ok = [&](uint32_t ref) {
+        if (ref >> 28) return false;
+        const uint32_t t = MRT_REF_TYPE(ref), i = MRT_REF_INDEX(ref);
+        switch (t) {
+        case MRT_T_SPHERE: return i < d.n_sphere;
+        case MRT_T_RECT_XY: case MRT_T_RECT_XZ: case MRT_T_RECT_YZ: return i < d.n_rect;
+        case MRT_T_LIST: return i < d.n_list;
+        case MRT_T_BVH: return i < d.n_bvh;
+        case MRT_T_NODE2: return i < d.n_node2;
+        case MRT_T_TRANSLATE: return i < d.n_xlate;
+        case MRT_T_ROTATE_Y: return i < d.n_rot;
+        case MRT_T_VOLUME: return i < d.n_vol;
+        case MRT_T_TRILEAF: return i < d.n_trileaf;
+        default: return false;
+        }
+    };
+    // materials and textures
+    for (uint32_t i = 0; i < d.n_tex; i++) {
+        const MrtF4 &t = d.tex[i];
+        const uint32_t kind = u(t.x);
+        if (kind > MRT_X_IMAGE) return fail("texture kind out of range");
+        if (kind == MRT_X_CHECKER && (u(t.y) >= d.n_tex || u(t.z) >= d.n_tex || u(t.y) == i || u(t.z) == i)) return fail("checker texture refers outside the texture table");
+        if (kind == MRT_X_PERLIN && (!d.perlin_vec || !d.perlin_perm)) return fail("perlin texture without perlin tables");
+        if (kind == MRT_X_IMAGE) {
+            const uint64_t w = u(t.y), h = u(t.z), off = u(t.w);
+            if (!w || !h || off + w * h * 3u > d.n_image_bytes) return fail("image texture outside the image table");
+        }
+    }
+    for (uint32_t i = 0; i < d.n_tex; i++) {   // checker chains must end (no cycles): follow at most n_tex links
+        uint32_t t = i, steps = 0;
+        while (u(d.tex[t].x) == MRT_X_CHECKER) { t = u(d.tex[t].y); if (++steps > d.n_tex) return fail("checker textures form a cycle"); }
+    }
+    for (uint32_t i = 0; i < d.n_mat; i++) {
+        if ((u(d.mat[i].x) & 0xFFu) > MRT_M_LIGHT) return fail("material kind out of range");
+        if (u(d.mat[i].y) >= d.n_tex && (u(d.mat[i].x) & 0xFFu) != MRT_M_DIELECTRIC) return fail("material refers outside the texture table");
+    }
+    auto mat_ok = [&](uint32_t m) { return m < d.n_mat; };
+    for (uint32_t i = 0; i < d.n_sphere; i++) if (!mat_ok(u(d.sphere[3 * i + 1].w) & 0x7FFFFFFFu)) return fail("sphere material out of range");
+    for (uint32_t i = 0; i < d.n_rect; i++) if (!mat_ok(u(d.rect[2 * i + 1].z))) return fail("rect material out of range");
+    for (uint32_t i = 0; i < d.n_tri; i++) if (!mat_ok(u(d.tri[3 * i].w))) return fail("triangle material out of range");
+    for (uint32_t i = 0; i < d.n_vol; i++) if (!mat_ok(u(d.vol[i].z)) || !ref_ok(u(d.vol[i].x))) return fail("volume refers outside its tables");
+    for (uint32_t i = 0; i < d.n_trileaf; i++) {
+        const uint64_t first = d.trileaf[2 * i], cnt = d.trileaf[2 * i + 1];
+        if (first + cnt > d.n_tri) return fail("triangle leaf outside the triangle table");
+    }
+    for (uint32_t i = 0; i < d.n_list; i++) {
+        uint32_t ci = u(d.list[2 * i].w);
+        for (;; ci++) {
+            if (ci >= d.n_child) return fail("list children not terminated inside the child table");
+            if (MRT_REF_TYPE(d.child[ci]) == MRT_T_END) break;
+            if (!ref_ok(d.child[ci])) return fail("list child refers outside its table");
+        }
+    }
+    for (uint32_t i = 0; i < d.n_bvh; i++) if (!ref_ok(u(d.bvh[2 * i].w))) return fail("tree root refers outside its table");
+    for (uint32_t i = 0; i < d.n_node2; i++) {
+        const uint32_t l = u(d.node2[4 * i].w) & 0x0FFFFFFFu, r = u(d.node2[4 * i + 1].w) & 0x0FFFFFFFu, fl = u(d.node2[4 * i + 2].w);
+        if (!ref_ok(l) || !ref_ok(r)) return fail("tree node child refers outside its table");
+        auto kind = [](uint32_t ref) { return MRT_REF_TYPE(ref) == MRT_T_NODE2 ? 0u : (MRT_REF_TYPE(ref) == MRT_T_TRILEAF ? 2u : 1u); };
+        if (((fl >> 2) & 3u) != kind(l) || ((fl >> 4) & 3u) != kind(r)) return fail("tree node flags disagree with its children");
+    }
+    for (uint32_t i = 0; i < d.n_xlate; i++) if (!ref_ok(u(d.xlate[3 * i].w))) return fail("translate child refers outside its table");
+    for (uint32_t i = 0; i < d.n_rot; i++) if (!ref_ok(u(d.rot[3 * i].w))) return fail("rotate_y child refers outside its table");
+    for (uint32_t i = 0; i < d.n_lights; i++) {
+        const uint32_t t = MRT_REF_TYPE(d.lights[i]);
+        if (!ref_ok(d.lights[i]) || t > MRT_T_RECT_YZ) return fail("light list entry is not a primitive of the scene");
+    }
+    if (!ref_ok(d.root)) return fail("root refers outside its table");
+    // depth of the traversal stack (mirrors Flattener::depth) with cycle / blow-up protection
+    uint64_t visits = 0;
+    const uint64_t visit_cap = 64ull * ((uint64_t) d.n_child + d.n_list + d.n_node2 + d.n_bvh + d.n_xlate + d.n_rot + d.n_vol + 16u);
+    bool bad = false;
+    bool coop = false;   // second pass: trees cost no per-lane stack (stack_words_coop)
+    auto depth = [&](uint32_t ref, uint32_t level, auto &&self) -> uint32_t {
+        if (bad) return 0;
+        if (level > 512 || ++visits > visit_cap) { bad = true; return 0; }
+        const uint32_t t = MRT_REF_TYPE(ref), i = MRT_REF_INDEX(ref);
+        switch (t) {
+        case MRT_T_LIST: {
+            uint32_t m = 0;
+            for (uint32_t ci = u(d.list[2 * i].w); MRT_REF_TYPE(d.child[ci]) != MRT_T_END; ci++)
+                if (MRT_REF_TYPE(d.child[ci]) > MRT_T_RECT_YZ) m = std::max(m, self(d.child[ci], level + 1, self));
+            return 1 + m;
+        }
+        case MRT_T_BVH: return coop ? 0u : self(u(d.bvh[2 * i].w), level + 1, self);
+        case MRT_T_NODE2: return 1 + std::max(self(u(d.node2[4 * i].w) & 0x0FFFFFFFu, level + 1, self), self(u(d.node2[4 * i + 1].w) & 0x0FFFFFFFu, level + 1, self));
+        case MRT_T_TRANSLATE: return 11 + self(u(d.xlate[3 * i].w), level + 1, self);
+        case MRT_T_ROTATE_Y: return 11 + self(u(d.rot[3 * i].w), level + 1, self);
+        case MRT_T_VOLUME: return 1 + self(u(d.vol[i].x), level + 1, self);
+        default: return 0;   // primitives (only legal as list children; elsewhere the traversal ignores them) and triangle leaves
+        }
+    };
+    const uint32_t need = depth(d.root, 0, depth) + 2;
+    if (bad) return fail("the object graph is cyclic or unreasonably deep");
+    if (stack_words_needed) *stack_words_needed = need;
+    if (d.stack_words && d.stack_words < need) return fail("stack_words is smaller than the scene's traversal depth");
+    if (d.stack_words > 1024u || need > 1024u) return fail("traversal stack deeper than 1024 words");
+    if (d.stack_words_coop) {
+        if (!coop_trees_supported(d)) return fail("stack_words_coop set although the trees do not qualify");
+        coop = true;
+        visits = 0;
+        if (d.stack_words_coop < depth(d.root, 0, depth) + 2 || d.stack_words_coop > 1024u) return fail("stack_words_coop is smaller than the scene needs");
+    }
+    return true;
+}
+
 bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &opt) {
     FlatScene &o = *out;
     o = FlatScene();

@@ -1,11 +1,13 @@
 // Host half of the C ABI (include/mrt_gpu.h): error string, command-line
 // parameters (cmdline_parser.cpp restated: same options, defaults, range checks
 // and warnings) and scene construction / flattening.
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <limits>
+#include <new>
 #include <string>
 
 #include "mrt_gpu.h"
@@ -40,92 +42,97 @@ extern "C" void mrt_params_default(MrtParams *p) {   // cmdline_parser.h:5-18
     strcpy(p->asset_dir, "assets");
 }
 
+// Option table: one descriptor per command-line option -- the reference's options (cmdline_parser.cpp:90-104: same names,
+// same defaults via mrt_params_default, same accepted ranges) and the four this front end adds.  One pass over argv; like the
+// reference, the FIRST occurrence of an option counts, a value outside the range or a missing value leaves the default in
+// place and prints a warning, and arguments that are not options are ignored.
 namespace {
-template <typename T> T read_value(char *arg);
-template <> float read_value<float>(char *arg) { return strtof(arg, nullptr); }
-template <> uint32_t read_value<uint32_t>(char *arg) { return (uint32_t) strtoul(arg, nullptr, 0); }
-template <> uint64_t read_value<uint64_t>(char *arg) { return (uint64_t) strtoull(arg, nullptr, 0); }
+enum class OptType { U32, U64, F32, Flag, Text };
+struct OptDesc {
+    const char *name;
+    OptType type;
+    size_t offset;        // field of MrtParams
+    double lo, hi;        // accepted range (numbers)
+    size_t text_cap;      // Text: capacity of the destination
+    const char *operand;  // help: what follows the option
+    const char *help;
+};
+#define MRT_OPT_FIELD(f) offsetof(MrtParams, f)
+constexpr double kU32Max = 4294967295.0;
+const OptDesc kOptions[] = {
+    {"-width", OptType::U32, MRT_OPT_FIELD(window_width), 1, kU32Max, 0, "<pixels>", "image width"},
+    {"-height", OptType::U32, MRT_OPT_FIELD(window_height), 1, kU32Max, 0, "<pixels>", "image height"},
+    {"-samples", OptType::U32, MRT_OPT_FIELD(samples_per_pixel), 1, kU32Max, 0, "<n>", "samples per pixel (rounded down to a square number)"},
+    {"-depth", OptType::U32, MRT_OPT_FIELD(max_bounces), 0, kU32Max, 0, "<n>", "bounce limit of a path"},
+    {"-maxlum", OptType::F32, MRT_OPT_FIELD(max_luminance), 1.17549435e-38 /* numeric_limits<float>::min(), cmdline_parser.cpp:41 */, 3.4028234e38, 0, "<x>", "luminance above which a pixel is scaled down (biased)"},
+    {"-threads", OptType::U32, MRT_OPT_FIELD(num_threads), 0, kU32Max, 0, "<n>", "CPU worker threads of the reference; accepted, unused by the GPU renderer"},
+    {"-tilesize", OptType::U32, MRT_OPT_FIELD(tile_size), 1, kU32Max, 0, "<pixels>", "tile edge of the reference's work queue; accepted, unused"},
+    {"-mode", OptType::U32, MRT_OPT_FIELD(threading_mode), 0, 1, 0, "0|1", "0: all samples in one launch, 1: progressive passes"},
+    {"-scene", OptType::U32, MRT_OPT_FIELD(scene_select), 0, 8, 0, "0..8", "which of the nine scenes"},
+    {"-delay", OptType::Flag, MRT_OPT_FIELD(delay), 0, 0, 0, "", "wait for a key press before starting (reference option; no effect headless)"},
+    {"-gpus", OptType::U32, MRT_OPT_FIELD(num_gpus), 1, 64, 0, "<n>", "GPUs to split the samples per pixel across"},
+    {"-seed", OptType::U64, MRT_OPT_FIELD(seed), 0, 1.8446744073709552e19, 0, "<n>", "PCG32 initstate of the per-(pixel, sample) streams"},
+    {"-assets", OptType::Text, MRT_OPT_FIELD(asset_dir), 0, 0, sizeof(MrtParams::asset_dir), "<dir>", "directory holding earthmap.ppm and obj/"},
+    {"-out", OptType::Text, MRT_OPT_FIELD(out_path), 0, 0, sizeof(MrtParams::out_path), "<file>", "image file: .ppm (tone mapped) or .pfm (linear)"},
+};
+constexpr size_t kNumOptions = sizeof(kOptions) / sizeof(kOptions[0]);
 
-// cmdline_parser.cpp:40-62
-template <typename T>
-int read_parameter(int argc, char **argv, const char *parameter, T *res, T min = std::numeric_limits<T>::min(),
-                   T max = std::numeric_limits<T>::max()) {
-    for (int i = 1; i < argc; i++) {
-        if (strcmp(parameter, argv[i]) == 0) {
-            if ((i + 1) == argc) {
-                std::cout << "Warning: Missing value for parameter '" << parameter << "'." << std::endl;
-                return 0;
-            }
-            T p = read_value<T>(argv[i + 1]);
-            if ((p < min) || (p > max)) {
-                std::cout << "Warning: Invalid value for parameter '" << parameter << "', must be in [" << min << ", " << max << "]."
-                          << std::endl;
-                return 0;
-            }
-            *res = p;
-            return i;
-        }
+const OptDesc *find_option(const char *arg, size_t *index) {
+    for (size_t i = 0; i < kNumOptions; i++)
+        if (!strcmp(arg, kOptions[i].name)) { *index = i; return &kOptions[i]; }
+    return nullptr;
+}
+bool wants_help(const char *arg) { return !strcmp(arg, "-help") || !strcmp(arg, "--help") || !strcmp(arg, "-?"); }
+
+void print_usage() {
+    printf("usage: mrt_b200 [options]\n");
+    for (size_t i = 0; i < kNumOptions; i++) {
+        const OptDesc &o = kOptions[i];
+        printf("  %-10s %-9s %s", o.name, o.operand, o.help);
+        if (o.type == OptType::U32 && o.hi < kU32Max) printf(" [%.0f, %.0f]", o.lo, o.hi);
+        printf("\n");
     }
-    return 0;
 }
-int check_parameter(int argc, char **argv, const char *parameter) {   // cmdline_parser.cpp:64-71
-    for (int i = 1; i < argc; i++)
-        if (strcmp(parameter, argv[i]) == 0) return i;
-    return 0;
-}
-int read_string(int argc, char **argv, const char *parameter, char *dst, size_t cap) {
-    int i = check_parameter(argc, argv, parameter);
-    if (!i) return 0;
-    if (i + 1 == argc) {
-        std::cout << "Warning: Missing value for parameter '" << parameter << "'." << std::endl;
-        return 0;
+
+// Stores the operand of option `o` into `p`; false (with a message) if it is not acceptable.
+bool store_operand(const OptDesc &o, const char *text, MrtParams *p) {
+    char *field = reinterpret_cast<char *>(p) + o.offset;
+    double as_number = 0;
+    switch (o.type) {
+    case OptType::U32: { const uint32_t v = (uint32_t) strtoul(text, nullptr, 0); as_number = v; if (as_number >= o.lo && as_number <= o.hi) { memcpy(field, &v, sizeof(v)); return true; } break; }
+    case OptType::U64: { const uint64_t v = (uint64_t) strtoull(text, nullptr, 0); memcpy(field, &v, sizeof(v)); return true; }
+    case OptType::F32: { const float v = strtof(text, nullptr); as_number = v; if (as_number >= o.lo && as_number <= o.hi) { memcpy(field, &v, sizeof(v)); return true; } break; }
+    case OptType::Text: snprintf(field, o.text_cap, "%s", text); return true;
+    case OptType::Flag: return true;
     }
-    strncpy(dst, argv[i + 1], cap - 1);
-    dst[cap - 1] = 0;
-    return i;
-}
-void print_help() {   // cmdline_parser.cpp:107-122 (+ the new options)
-    printf("\n"
-           "PARAMETERS:\n"
-           "  -width    \t<value>\t\tWindow width\n"
-           "  -height   \t<value>\t\tWindow height\n"
-           "  -samples  \t<value>\t\tSamples per pixel\n"
-           "  -depth    \t<value>\t\tMaximum bounce depth per primary ray\n"
-           "  -maxlum   \t<value>\t\tClamp maximum luminance (introduces bias)\n"
-           "  -threads  \t<value>\t\tNumber of execution threads (0 selects maximum hardware threads)\n"
-           "  -tilesize \t<value>\t\tSize of image tiles (threads operate on tiles)\n"
-           "  -mode     \t[0, 1]\t\tThreading/queue mode (0 for sequential, 1 for dynamic sampling)\n"
-           "  -scene    \t[0, %i]\t\tSelect the scene\n"
-           "  -delay    \t\t\tDelay start until keypress\n"
-           "  -gpus     \t<value>\t\tNumber of GPUs (samples per pixel are split across them)\n"
-           "  -seed     \t<value>\t\tPCG32 initstate of the per-(pixel, sample) streams\n"
-           "  -assets   \t<dir>\t\tDirectory with earthmap.ppm and obj/\n"
-           "  -out      \t<file>\t\tWrite the image (.ppm tone-mapped, .pfm linear)\n",
-           8);
+    printf("warning: %s %s is outside [%.9g, %.9g]; keeping the default\n", o.name, text, o.lo, o.hi);
+    return false;
 }
 }  // namespace
 
 extern "C" int mrt_params_parse(int argc, char **argv, MrtParams *out) {
-    if (check_parameter(argc, argv, "-help") || check_parameter(argc, argv, "--help") || check_parameter(argc, argv, "-?")) {
-        print_help();
-        return 1;
-    }
+    for (int i = 1; i < argc; i++)
+        if (wants_help(argv[i])) { print_usage(); return 1; }
     MrtParams p;
     mrt_params_default(&p);
-    if (read_parameter<uint32_t>(argc, argv, "-width", &p.window_width, 1u)) p.buffer_width = p.window_width;
-    if (read_parameter<uint32_t>(argc, argv, "-height", &p.window_height, 1u)) p.buffer_height = p.window_height;
-    read_parameter<uint32_t>(argc, argv, "-samples", &p.samples_per_pixel, 1u);
-    read_parameter<uint32_t>(argc, argv, "-tilesize", &p.tile_size, 1u);
-    read_parameter<uint32_t>(argc, argv, "-threads", &p.num_threads);
-    read_parameter<uint32_t>(argc, argv, "-depth", &p.max_bounces);
-    read_parameter<uint32_t>(argc, argv, "-scene", &p.scene_select, 0u, 8u);
-    read_parameter<uint32_t>(argc, argv, "-mode", &p.threading_mode, 0u, 1u);
-    read_parameter<float>(argc, argv, "-maxlum", &p.max_luminance);
-    if (check_parameter(argc, argv, "-delay")) p.delay = 1;
-    read_parameter<uint32_t>(argc, argv, "-gpus", &p.num_gpus, 1u, 64u);
-    read_parameter<uint64_t>(argc, argv, "-seed", &p.seed);
-    read_string(argc, argv, "-assets", p.asset_dir, sizeof(p.asset_dir));
-    read_string(argc, argv, "-out", p.out_path, sizeof(p.out_path));
+    bool seen[kNumOptions] = {};
+    for (int i = 1; i < argc; i++) {
+        size_t k = 0;
+        const OptDesc *o = find_option(argv[i], &k);
+        if (!o) continue;                      // not an option: ignored, as in the reference
+        const bool first = !seen[k];
+        seen[k] = true;
+        if (o->type == OptType::Flag) {
+            if (first) { const uint32_t one = 1; memcpy(reinterpret_cast<char *>(&p) + o->offset, &one, sizeof(one)); }
+            continue;
+        }
+        if (i + 1 >= argc) { if (first) printf("warning: %s needs a value; keeping the default\n", o->name); break; }
+        i++;                                   // the operand is consumed even when a repeated option is ignored
+        if (first) store_operand(*o, argv[i], &p);
+    }
+    // the reference renders into a buffer of the window's size (cmdline_parser.cpp:92-93)
+    p.buffer_width = p.window_width;
+    p.buffer_height = p.window_height;
     *out = p;
     return 0;
 }
@@ -170,17 +177,24 @@ extern "C" int mrt_scene_dump(const MrtHostScene *s, const char *path) {
 }
 
 // ---------------------------------------------------------------- scene file
+// "MRTSCN2": magic, sizeof(MrtSceneDesc) of the writer, the description with every pointer field zeroed, then each table as
+// (uint64 count, raw records).  A file is checked structurally before it is accepted (validate_scene_desc): table sizes against
+// the counts, every reference inside its table, terminated child runs, Perlin tables of 256 / 768 entries, stack depth.
 namespace {
-const char kMagic[8] = {'M', 'R', 'T', 'S', 'C', 'N', '1', 0};
+const char kMagic[8] = {'M', 'R', 'T', 'S', 'C', 'N', '2', 0};
 template <typename T> bool put(FILE *f, const std::vector<T> &v) {
     uint64_t n = v.size();
     return fwrite(&n, sizeof(n), 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
 }
-template <typename T> bool get(FILE *f, std::vector<T> &v) {
+template <typename T> bool get(FILE *f, std::vector<T> &v, uint64_t max_count) {
     uint64_t n = 0;
-    if (fread(&n, sizeof(n), 1, f) != 1 || n > (1ull << 34) / sizeof(T)) return false;
+    if (fread(&n, sizeof(n), 1, f) != 1 || n > max_count) return false;
     v.resize(n);
     return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+void clear_pointers(MrtSceneDesc &d) {
+    d.lights = nullptr; d.sphere = d.rect = d.list = d.bvh = d.node2 = d.tri = d.trin = d.xlate = d.rot = d.vol = d.mat = d.tex = d.perlin_vec = nullptr;
+    d.child = d.trileaf = nullptr; d.perlin_perm = nullptr; d.image = nullptr;
 }
 void rebind(FlatScene &o) {   // pointers of the description follow the vectors
     MrtSceneDesc &d = o.desc;
@@ -192,6 +206,22 @@ void rebind(FlatScene &o) {   // pointers of the description follow the vectors
     d.perlin_perm = o.perlin_perm.empty() ? nullptr : o.perlin_perm.data();
     d.image = o.image.empty() ? nullptr : o.image.data();
 }
+bool read_scene_file(FILE *f, FlatScene &o) {
+    char magic[8];
+    uint64_t desc_size = 0;
+    if (fread(magic, 8, 1, f) != 1 || memcmp(magic, kMagic, 8) != 0) return false;
+    if (fread(&desc_size, sizeof(desc_size), 1, f) != 1 || desc_size != sizeof(MrtSceneDesc)) return false;
+    if (fread(&o.desc, sizeof(o.desc), 1, f) != 1) return false;
+    clear_pointers(o.desc);
+    const MrtSceneDesc &d = o.desc;
+    // every table is read with its count bounded by what the description announces (no attacker-sized allocations)
+    return get(f, o.sphere, (uint64_t) d.n_sphere * 3) && get(f, o.rect, (uint64_t) d.n_rect * 2) && get(f, o.list, (uint64_t) d.n_list * 2) &&
+           get(f, o.child, d.n_child) && get(f, o.bvh, (uint64_t) d.n_bvh * 2) && get(f, o.node2, (uint64_t) d.n_node2 * 4) &&
+           get(f, o.trileaf, (uint64_t) d.n_trileaf * 2) && get(f, o.tri, (uint64_t) d.n_tri * 3) && get(f, o.trin, (uint64_t) d.n_tri * 3) &&
+           get(f, o.xlate, (uint64_t) d.n_xlate * 3) && get(f, o.rot, (uint64_t) d.n_rot * 3) && get(f, o.vol, d.n_vol) && get(f, o.mat, d.n_mat) &&
+           get(f, o.tex, d.n_tex) && get(f, o.perlin_vec, 256) && get(f, o.perlin_perm, 768) && get(f, o.image, d.n_image_bytes) &&
+           get(f, o.lights, d.n_lights);
+}
 }  // namespace
 
 extern "C" int mrt_scene_save(const MrtHostScene *s, const char *path) {
@@ -199,8 +229,10 @@ extern "C" int mrt_scene_save(const MrtHostScene *s, const char *path) {
     FILE *f = fopen(path, "wb");
     if (!f) { set_error(std::string("cannot open ") + path); return MRT_E_INVALID; }
     const FlatScene &o = s->flat;
-    MrtSceneDesc d = o.desc;   // scalar part; pointers are meaningless in the file
-    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&d, sizeof(d), 1, f) == 1;
+    MrtSceneDesc d = o.desc;   // scalar part; host pointers are meaningless in a file and are not written
+    clear_pointers(d);
+    const uint64_t desc_size = sizeof(MrtSceneDesc);
+    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&desc_size, sizeof(desc_size), 1, f) == 1 && fwrite(&d, sizeof(d), 1, f) == 1;
     ok = ok && put(f, o.sphere) && put(f, o.rect) && put(f, o.list) && put(f, o.child) && put(f, o.bvh) && put(f, o.node2) &&
          put(f, o.trileaf) && put(f, o.tri) && put(f, o.trin) && put(f, o.xlate) && put(f, o.rot) && put(f, o.vol) && put(f, o.mat) &&
          put(f, o.tex) && put(f, o.perlin_vec) && put(f, o.perlin_perm) && put(f, o.image) && put(f, o.lights);
@@ -218,20 +250,30 @@ extern "C" int mrt_scene_load(const char *path, MrtHostScene **out) {
     if (!s) { fclose(f); set_error("out of memory"); return MRT_E_INVALID; }
     s->has_graph = false;
     FlatScene &o = s->flat;
-    char magic[8];
-    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&o.desc, sizeof(o.desc), 1, f) == 1;
-    ok = ok && get(f, o.sphere) && get(f, o.rect) && get(f, o.list) && get(f, o.child) && get(f, o.bvh) && get(f, o.node2) &&
-         get(f, o.trileaf) && get(f, o.tri) && get(f, o.trin) && get(f, o.xlate) && get(f, o.rot) && get(f, o.vol) && get(f, o.mat) &&
-         get(f, o.tex) && get(f, o.perlin_vec) && get(f, o.perlin_perm) && get(f, o.image) && get(f, o.lights);
+    bool ok = false;
+    std::string why = "not a valid MRTSCN2 file";
+    try {   // nothing may throw across the C ABI (a table count the machine cannot allocate)
+        ok = read_scene_file(f, o);
+    } catch (const std::bad_alloc &) {
+        ok = false;
+        why = "out of memory";
+    }
     fclose(f);
     const MrtSceneDesc &d = o.desc;
     ok = ok && o.sphere.size() == (size_t) d.n_sphere * 3 && o.rect.size() == (size_t) d.n_rect * 2 && o.list.size() == (size_t) d.n_list * 2 &&
          o.child.size() == d.n_child && o.bvh.size() == (size_t) d.n_bvh * 2 && o.node2.size() == (size_t) d.n_node2 * 4 &&
          o.trileaf.size() == (size_t) d.n_trileaf * 2 && o.tri.size() == (size_t) d.n_tri * 3 && o.trin.size() == o.tri.size() &&
          o.xlate.size() == (size_t) d.n_xlate * 3 && o.rot.size() == (size_t) d.n_rot * 3 && o.vol.size() == d.n_vol && o.mat.size() == d.n_mat &&
-         o.tex.size() == d.n_tex && o.image.size() == d.n_image_bytes && o.lights.size() == d.n_lights;
-    if (!ok) { delete s; set_error(std::string("not a valid MRTSCN1 file: ") + path); return MRT_E_SCENE; }
-    rebind(o);
+         o.tex.size() == d.n_tex && o.image.size() == d.n_image_bytes && o.lights.size() == d.n_lights &&
+         (o.perlin_vec.empty() || o.perlin_vec.size() == 256) && (o.perlin_perm.empty() || o.perlin_perm.size() == 768) &&
+         o.perlin_vec.empty() == o.perlin_perm.empty();
+    if (ok) {
+        rebind(o);
+        std::string detail;
+        ok = validate_scene_desc(o.desc, &detail, nullptr);
+        if (!ok) why = detail;
+    }
+    if (!ok) { delete s; set_error(why + ": " + path); return MRT_E_SCENE; }
     *out = s;
     return MRT_OK;
 }

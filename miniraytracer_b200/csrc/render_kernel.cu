@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "gpu_internal.h"
+#include "scene_graph.h"
 #include "render_kernels.cuh"
 #include "render_variants.h"
 
@@ -359,9 +360,12 @@ static void find_classifier_boxes(const MrtSceneDesc *d, MrtScene *s) {
 extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     if (!d || !out) { set_error("mrt_gpu_scene_upload: null argument"); return MRT_E_INVALID; }
     *out = nullptr;
+    {   // a description built by a caller (or read from a file) is checked before anything of it reaches the device
+        std::string why;
+        if (!validate_scene_desc(*d, &why, nullptr)) { set_error("mrt_gpu_scene_upload: invalid scene description: " + why); return MRT_E_SCENE; }
+    }
     MrtScene *s = new (std::nothrow) MrtScene();
     if (!s) { set_error("out of memory"); return MRT_E_INVALID; }
-    int rc = MRT_OK;
     auto fail = [&](int code) { mrt_gpu_destroy(s); return code; };
     if (cudaGetDevice(&s->device) != cudaSuccess) { set_error("no CUDA device (mrt_gpu_init not called?)"); return fail(MRT_E_CUDA); }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);

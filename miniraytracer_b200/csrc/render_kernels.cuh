@@ -349,7 +349,6 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     // which path, the chunk size does not depend on the samples per pixel, and no shared memory is needed for sums
     float4 *stage = a.stage + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) a.stage_items;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t n_pixels = a.n_pixels;
     const uint32_t ns = a.s_end - a.s_begin;
     unsigned long long rays = 0, nonfinite = 0, iters = 0;
 

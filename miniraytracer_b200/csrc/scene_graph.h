@@ -189,6 +189,7 @@ struct FlattenOptions {
     bool cull_boxes = true;   // conservative cull boxes on translate nodes (trace_core.h: cull_miss); off = A/B for the parity test
 };
 bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &opt = FlattenOptions());
-bool coop_trees_supported(const MrtSceneDesc &d);   // do the BVH trees qualify for the warp-cooperative traversal (coop_tree.cuh)?
+bool coop_trees_supported(const MrtSceneDesc &d);
+bool validate_scene_desc(const MrtSceneDesc &d, std::string *err, uint32_t *stack_words_needed);   // structural check (scene files, caller-built descriptions)   // do the BVH trees qualify for the warp-cooperative traversal (coop_tree.cuh)?
 
 }  // namespace mrt

@@ -56,13 +56,22 @@ class ProgressiveReducer:
     into a bound accumulator; in the CPU tests a stand-in.  After every pass the cumulative local accumulator is
     snapshotted into one of two staging buffers and all-reduced asynchronously while the next pass renders; `preview`
     receives (pass_index, reduced_accumulator) once that reduction has finished (one pass late, by design).
-    On CUDA the snapshot and the collective run on a side stream ordered after the render stream by an event.
+    On CUDA the snapshot and the collective run on a side stream ordered after the RENDER stream by an event.  The render
+    stream is `stream` (a torch.cuda.Stream; default: the current stream at construction): `render_pass` must launch on it --
+    i.e. the renderer's mrt_gpu_set_stream must have been given this stream's handle; pass `renderer=` to have that done here.
+    A renderer left on the legacy NULL stream while torch runs on a non-default stream would not be ordered against the
+    snapshot copy, so the contract is explicit.
     """
 
-    def __init__(self, acc, render_pass, preview=None):
+    def __init__(self, acc, render_pass, preview=None, stream=None, renderer=None):
         self.acc = acc
         self.render_pass = render_pass
         self.preview = preview
+        self.render_stream = None
+        if acc.is_cuda:
+            self.render_stream = stream if stream is not None else torch.cuda.current_stream(acc.device)
+            if renderer is not None:
+                renderer.set_stream(self.render_stream.cuda_stream)
         self.staging = [torch.empty_like(acc), torch.empty_like(acc)]
         self.cuda = acc.is_cuda
         self.side = torch.cuda.Stream(device=acc.device) if self.cuda else None
@@ -76,7 +85,7 @@ class ProgressiveReducer:
         buf = self.staging[p & 1]
         if self.cuda:
             ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(self.acc.device))
+            ready.record(self.render_stream)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ready)
                 buf.copy_(self.acc, non_blocking=True)
@@ -107,12 +116,16 @@ class ProgressiveReducer:
         return buf
 
     def run(self, schedule):
-        """Render all passes of `schedule` (list of (begin, end)); returns the fully reduced accumulator."""
+        """Render all passes of `schedule` (list of (begin, end)); returns the fully reduced accumulator (for an empty
+        schedule: the all-reduced accumulator as it stands)."""
+        if not schedule:
+            self._launch_reduce(0)
+            return self._finish_pending()
         last = None
         for p, (b, e) in enumerate(schedule):
             if e > b:
                 if self._snapshot_taken is not None:   # the previous snapshot must have read acc before it changes
-                    torch.cuda.current_stream(self.acc.device).wait_event(self._snapshot_taken)
+                    self.render_stream.wait_event(self._snapshot_taken)
                 self.render_pass(b, e, self.acc)      # pass p renders while pass p-1 is being reduced
             last = self._finish_pending() if self._pending is not None else last
             self._launch_reduce(p)

@@ -209,25 +209,31 @@ def test_binned_pool_renderer_parity(scene, w, h, spp, binned):
 
 def test_progressive_passes_single_gpu():
     """distributed.ProgressiveReducer on one GPU: sample-major passes accumulated into a bound torch accumulator with
-    the per-pass snapshot taken on a side stream; the last preview equals a one-shot render of all samples."""
+    the per-pass snapshot taken on a side stream; the last preview equals a one-shot render of all samples.  The renderer
+    runs on a NON-default torch stream that the reducer is told about (renderer=, stream=): snapshot and render are ordered
+    by events on that stream, not on whatever stream happens to be current."""
     import torch
     from miniraytracer_b200 import distributed as mdist
     w, h, spp, passes = 160, 90, 64, 4
     full, _ = _gpu_render(5, w, h, spp)
     hs = api.HostScene(5, w, h)
     r = api.Renderer(hs, 0)
+    render_stream = torch.cuda.Stream(device="cuda:0")
     acc = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda:0")
-    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     r.bind_accumulator(acc.data_ptr(), w, h)
     counts = []
 
     def render_pass(b, e, out):
         r.render_async(w, h, spp, sample_begin=b, sample_end=e, accumulate=True)
 
-    red = mdist.ProgressiveReducer(acc, render_pass, preview=lambda p, buf: counts.append(float(buf[..., 3].max().item())))
+    red = mdist.ProgressiveReducer(acc, render_pass, preview=lambda p, buf: counts.append(float(buf[..., 3].max().item())),
+                                   stream=render_stream, renderer=r)
     final = red.run(mdist.progressive_schedule(spp, 0, 1, passes))
     torch.cuda.synchronize()
     got = final.cpu().numpy()
+    empty = mdist.ProgressiveReducer(acc, render_pass, stream=render_stream, renderer=r).run([])
+    assert empty is not None and torch.equal(empty, acc)
     r.close(); hs.close()
     assert counts == [16.0, 32.0, 48.0, 64.0]
     np.testing.assert_array_equal(got[..., 3], full[..., 3])

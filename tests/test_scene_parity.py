@@ -90,3 +90,58 @@ def test_scene_file_round_trip(scene, tmp_path):
     hs.close(); ld.close()
     with pytest.raises(api.MrtError):
         api.HostScene.load(tmp_path / "missing.mrtscn")
+
+
+def test_scene_file_is_validated(tmp_path):
+    """A truncated or inconsistent scene file is rejected with a status code instead of being read out of bounds later
+    (mrt_scene_load -> validate_scene_desc): short tables, a missing child terminator, an out-of-range reference, a short
+    Perlin table, a stack depth smaller than the scene needs, a wrong header."""
+    import struct
+    hs = api.HostScene(7, 640, 360)     # trees, transforms, volumes, perlin + image textures
+    good = tmp_path / "good.mrtscn"
+    hs.save(good)
+    raw = bytearray(good.read_bytes())
+    hs.close()
+    api.HostScene.load(good).close()
+    desc_size = struct.unpack_from("<Q", raw, 8)[0]
+    import ctypes
+    assert desc_size == ctypes.sizeof(api.SceneDesc)
+
+    def expect_reject(data, name):
+        p = tmp_path / name
+        p.write_bytes(bytes(data))
+        with pytest.raises(api.MrtError):
+            api.HostScene.load(p)
+
+    expect_reject(raw[: len(raw) // 2], "truncated.mrtscn")
+    bad = bytearray(raw); bad[6:7] = b"1"                      # the old magic
+    expect_reject(bad, "magic.mrtscn")
+    bad = bytearray(raw); struct.pack_into("<Q", bad, 8, desc_size + 8)
+    expect_reject(bad, "descsize.mrtscn")
+    off = 16                                                    # the description starts after magic + size
+    root_off = off + api.SceneDesc.root.offset
+    bad = bytearray(raw); struct.pack_into("<I", bad, root_off, (4 << 24) | 0xFFFFF)   # a list index far outside the table
+    expect_reject(bad, "root.mrtscn")
+    sw_off = off + api.SceneDesc.stack_words.offset
+    bad = bytearray(raw); struct.pack_into("<I", bad, sw_off, 3)
+    expect_reject(bad, "stack.mrtscn")
+    # first table = spheres: count word right after the description; claim one record fewer
+    tbl = off + desc_size
+    n = struct.unpack_from("<Q", raw, tbl)[0]
+    bad = bytearray(raw); struct.pack_into("<Q", bad, tbl, n - 1)
+    expect_reject(bad, "count.mrtscn")
+    # child table: overwrite every END terminator
+    d = api.HostScene.load(good)
+    n_child = d.desc.contents.n_child
+    d.close()
+    pos = tbl
+    for elems, size in ((None, 16), (None, 16), (None, 16)):    # skip sphere, rect, list tables
+        cnt = struct.unpack_from("<Q", raw, pos)[0]
+        pos += 8 + cnt * size
+    assert struct.unpack_from("<Q", raw, pos)[0] == n_child
+    bad = bytearray(raw)
+    for i in range(n_child):
+        v = struct.unpack_from("<I", bad, pos + 8 + 4 * i)[0]
+        if (v >> 24) & 15 == 15:
+            struct.pack_into("<I", bad, pos + 8 + 4 * i, 0)     # sphere 0 instead of END
+    expect_reject(bad, "noterm.mrtscn")
