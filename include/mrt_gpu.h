@@ -156,6 +156,16 @@ int mrt_gpu_finalize_device(MrtScene *s, const void *acc_dev, void *out_dev, uin
 /* Copies the accumulator (finalize = 0) or the finalised image (finalize = 1) to
  * rgba_host (width*height*4 floats); blocks.  Replaces reading G_linearBackBuffer. */
 int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize);
+/* The reference's default worker draw2 (main.cpp:193-243, with work_queue_dynamic): sample-major passes and a RUNNING MEAN per
+ * pixel -- a non-finite sample is replaced by the mean so far (0 for the first sample), and the luminance clamp is applied after
+ * EVERY pass and feeds back into the mean (main.cpp:214-231).  mrt_gpu_running_mean_update applies one such pass: acc_dev holds one
+ * sample per pixel (a one-sample launch: w = 1 if finite), mean_dev (float4 per pixel) is updated in place; `pass` = 0 for the first.
+ * mrt_gpu_render_running_mean runs the whole thing for samples [sample_begin, sample_end) as one-sample launches into the scene's
+ * own buffers and copies the final mean to rgba_host (may be NULL; w = number of passes).  The plain accumulate path (sum / count,
+ * clamp once at the end) gives the same image unless a running mean crosses max_luminance on the way. */
+int mrt_gpu_running_mean_update(MrtScene *s, const void *acc_dev, void *mean_dev, uint32_t width, uint32_t height, uint32_t pass,
+                                float max_luminance);
+int mrt_gpu_render_running_mean(MrtScene *s, const MrtRenderParams *p, float *rgba_host);
 /* Adaptive logarithmic tone map + ARGB32 pack of the reference's preview loop
  * (main.cpp:416-444, vec3.h:327-333) from the finalised image; argb_host: width*height uint32. */
 int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host);

@@ -171,6 +171,8 @@ typedef struct MrtRenderParams {
 } MrtRenderParams;
 
 #define MRT_RENDER_ACCUMULATE 1u /* add to the accumulator instead of overwriting it */
+#define MRT_RENDER_CONTINUE 2u   /* this launch continues the previous one(s): ray / path statistics and the kernel-time window of
+                                    mrt_gpu_stats keep running instead of restarting */
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ class RenderStats(C.Structure):
 
 
 MRT_RENDER_ACCUMULATE = 1
+MRT_RENDER_CONTINUE = 2
 SCENE_ALL_LIGHTS = 0x100   # MRT_SCENE_ALL_LIGHTS: light list with both allocated entries (ceiling light + glass sphere)
 DEFAULT_SEED = 11350390909718046443  # main.cpp:302
 
@@ -90,7 +91,7 @@ EXPORTS = [
     "mrt_last_error", "mrt_params_default", "mrt_params_parse", "mrt_scene_create", "mrt_scene_desc",
     "mrt_scene_dump", "mrt_scene_save", "mrt_scene_load", "mrt_scene_free", "mrt_gpu_init", "mrt_gpu_scene_upload", "mrt_gpu_set_tuning", "mrt_gpu_set_stream",
     "mrt_gpu_bind_accumulator", "mrt_gpu_render_async", "mrt_gpu_poll", "mrt_gpu_wait", "mrt_gpu_stats",
-    "mrt_gpu_finalize_device", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_tonemap_device", "mrt_gpu_reduce_finalize", "mrt_gpu_cancel", "mrt_gpu_destroy",
+    "mrt_gpu_finalize_device", "mrt_gpu_running_mean_update", "mrt_gpu_render_running_mean", "mrt_gpu_readback", "mrt_gpu_tonemap", "mrt_gpu_tonemap_device", "mrt_gpu_reduce_finalize", "mrt_gpu_cancel", "mrt_gpu_destroy",
 ]
 
 
@@ -140,6 +141,8 @@ def load(build_if_missing=True):
     lib.mrt_gpu_stats.argtypes = [vp, C.POINTER(RenderStats)]
     lib.mrt_gpu_finalize_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_float]
     lib.mrt_gpu_readback.argtypes = [vp, vp, C.c_int]
+    lib.mrt_gpu_running_mean_update.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
+    lib.mrt_gpu_render_running_mean.argtypes = [vp, C.POINTER(RenderParams), vp]
     lib.mrt_gpu_tonemap.argtypes = [vp, vp]
     lib.mrt_gpu_tonemap_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32]
     lib.mrt_gpu_reduce_finalize.argtypes = [C.POINTER(vp), C.c_int, C.c_float, vp, vp]
@@ -258,6 +261,15 @@ class Renderer:
         _check(self._lib.mrt_gpu_render_async(self._h, C.byref(p)))
         self._size = (x1 - x0, y1 - y0) if crop else (width, height)
         return p
+
+    def render_running_mean(self, width, height, spp, depth=32, seed=DEFAULT_SEED, sample_begin=0, sample_end=None, max_luminance=1000.0):
+        """mrt_gpu_render_running_mean: draw2's sample-major passes with the per-pass clamped running mean; returns mean[h, w, 4]."""
+        n = grid_samples(spp)
+        p = RenderParams(width, height, n, sample_begin, n if sample_end is None else sample_end, depth, seed, max_luminance, 0, 0, 0, 0, 0)
+        out = np.empty((height, width, 4), dtype=np.float32)
+        _check(self._lib.mrt_gpu_render_running_mean(self._h, C.byref(p), out.ctypes.data_as(C.c_void_p)))
+        self._size = (width, height)
+        return out
 
     def poll(self):
         pct, rays = C.c_float(), C.c_uint64()

@@ -55,6 +55,8 @@ struct MrtScene {
     MrtRenderParams last;
     uint32_t last_tasks = 0, last_grid = 0, last_block = mrt::kBlock, last_smem = 0, last_mode = 0;
     bool last_coop = false;
+    bool final_is_running_mean = false;   // final_buf holds draw2's running mean (mrt_gpu_render_running_mean), not a finalised sum
+    uint64_t stat_samples = 0;    // samples per pixel covered by the statistics (several launches with MRT_RENDER_CONTINUE)
     uint32_t last_w = 0, last_h = 0;   // size of the rendered window = of the accumulator
     float4 *last_acc = nullptr;
     // pixel work order (Z-curve), rebuilt when the frame size changes

@@ -77,6 +77,10 @@ int main(int argc, char **argv) {
     // -mode 1 (work_queue_dynamic + draw2, main.cpp:350-354,193-243): sample-major passes, the image refines
     // progressively; here each pass is one launch that ACCUMULATES a slice of the samples (sum + count, so the
     // running mean of draw2 is the finalised accumulator after every pass).
+    // With one GPU -mode 1 is draw2 itself: one-sample passes and the running mean with its per-pass luminance clamp
+    // (mrt_gpu_render_running_mean).  With several GPUs the samples are sharded, which a clamped running mean over ALL
+    // samples cannot be; there the passes accumulate sums (identical unless a running mean crosses -maxlum on the way).
+    const bool running_mean = (p.threading_mode == 1) && G == 1;
     uint32_t passes = (p.threading_mode == 1) ? 8u : 1u;
     if (passes > N / G) passes = (N / G) ? (N / G) : 1u;   // at least one sample per pass and GPU
     uint64_t rays = 0, paths = 0, dropped = 0;
@@ -93,6 +97,15 @@ int main(int argc, char **argv) {
         kernel_ms += ms_max;
         return 0;
     };
+    if (running_mean) {
+        MrtRenderParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.width = W; rp.height = H; rp.samples = N; rp.sample_begin = 0; rp.sample_end = N;
+        rp.max_bounces = p.max_bounces; rp.seed = p.seed; rp.max_luminance = p.max_luminance;
+        mrt_gpu_init(0, nullptr);
+        if (mrt_gpu_render_running_mean(scenes[0], &rp, nullptr)) { fprintf(stderr, "error: %s\n", mrt_last_error()); return 1; }
+        passes = 0;
+    }
     for (uint32_t pass = 0; pass < passes; pass++) {
         if (pass && collect()) return 1;
         for (uint32_t g = 0; g < G; g++) {
@@ -139,7 +152,10 @@ int main(int argc, char **argv) {
         const bool pfm = len > 4 && !strcmp(p.out_path + len - 4, ".pfm");
         std::vector<float> rgba(pfm ? (size_t) W * H * 4 : 0);
         std::vector<uint32_t> argb(pfm ? 0 : (size_t) W * H);
-        if (mrt_gpu_reduce_finalize(scenes.data(), (int) G, p.max_luminance, pfm ? rgba.data() : nullptr, pfm ? nullptr : argb.data())) {
+        int rc_img;
+        if (running_mean) rc_img = pfm ? mrt_gpu_readback(scenes[0], rgba.data(), 1) : mrt_gpu_tonemap(scenes[0], argb.data());   // the running mean itself
+        else rc_img = mrt_gpu_reduce_finalize(scenes.data(), (int) G, p.max_luminance, pfm ? rgba.data() : nullptr, pfm ? nullptr : argb.data());
+        if (rc_img) {
             fprintf(stderr, "error: %s\n", mrt_last_error());
             return 1;
         }

@@ -37,6 +37,32 @@ __global__ void finalize_kernel(const float4 *acc, float4 *out, uint32_t n, floa
     out[i] = make_float4(r, g, b, a.w);
 }
 
+// --------------------------------------------------------------- draw2's pixel update
+// The reference's default worker (draw2, main.cpp:193-243) renders sample-major passes and keeps a RUNNING MEAN per pixel:
+// a non-finite sample is replaced by the mean so far (by 0 for the first sample), the mean advances by (c - mean) / (s + 1),
+// and the luminance clamp is applied after every pass and feeds back into the mean (main.cpp:214-231).  `acc` holds ONE
+// sample per pixel (a one-sample launch: xyz = the sample or 0, w = 1 if it was finite); `mean` is updated in place.
+__global__ void running_mean_kernel(const float4 *acc, float4 *mean, uint32_t n, uint32_t pass, float max_lum) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = acc[i];
+    const float4 m = mean[i];
+    float r = a.x, g = a.y, b = a.z;
+    if (!(a.w > 0)) { r = pass ? m.x : 0.0f; g = pass ? m.y : 0.0f; b = pass ? m.z : 0.0f; }
+    if (pass) {
+        const float k = __fdiv_rn(1.0f, __fadd_rn((float) pass, 1.0f));
+        r = __fadd_rn(m.x, __fmul_rn(__fsub_rn(r, m.x), k));
+        g = __fadd_rn(m.y, __fmul_rn(__fsub_rn(g, m.y), k));
+        b = __fadd_rn(m.z, __fmul_rn(__fsub_rn(b, m.z), k));
+    }
+    const float lum = __fadd_rn(__fadd_rn(__fmul_rn(r, 0.212655f), __fmul_rn(g, 0.715158f)), __fmul_rn(b, 0.072187f));
+    if (lum > max_lum) {
+        const float k = __fdiv_rn(max_lum, lum);
+        r = __fmul_rn(r, k); g = __fmul_rn(g, k); b = __fmul_rn(b, k);
+    }
+    mean[i] = make_float4(r, g, b, (float) (pass + 1u));
+}
+
 // --------------------------------------------------------------- tone map
 // Adaptive logarithmic mapping of the reference's preview loop (main.cpp:416-444)
 __global__ void max_luminance_kernel(const float4 *img, uint32_t n, unsigned int *max_bits) {
@@ -694,8 +720,14 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     }
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), s->stream));
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    s->final_is_running_mean = false;
+    const bool cont = (p->flags & MRT_RENDER_CONTINUE) && s->rendered;
+    if (!cont) {
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), s->stream));
+        CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+        s->stat_samples = 0;
+    }
+    s->stat_samples += ns;
     void *kargs[] = {(void *) &a};
     CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -756,7 +788,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     CUDA_TRY(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->rays = c[0];
-    out->paths = (uint64_t) s->last_w * s->last_h * (s->last.sample_end - s->last.sample_begin);
+    out->paths = (uint64_t) s->last_w * s->last_h * s->stat_samples;
     out->nonfinite = c[2];
     out->warp_iterations = c[1];
     CUDA_TRY(cudaEventElapsedTime(&out->kernel_ms, s->ev0, s->ev1));
@@ -799,14 +831,55 @@ extern "C" int mrt_gpu_readback(MrtScene *s, float *rgba_host, int finalize) {
     const size_t n = (size_t) s->last_w * s->last_h;
     const float4 *src = s->last_acc;
     if (finalize) {
-        int rc = ensure_final(s, n);
-        if (rc) return rc;
-        rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
-        if (rc) return rc;
+        if (!s->final_is_running_mean) {
+            int rc = ensure_final(s, n);
+            if (rc) return rc;
+            rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
+            if (rc) return rc;
+        }
         src = s->final_buf;
     }
     CUDA_TRY(cudaMemcpyAsync(rgba_host, src, n * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MRT_OK;
+}
+
+extern "C" int mrt_gpu_running_mean_update(MrtScene *s, const void *acc_dev, void *mean_dev, uint32_t width, uint32_t height, uint32_t pass,
+                                           float max_luminance) {
+    if (!s || !acc_dev || !mean_dev) { set_error("mrt_gpu_running_mean_update: null argument"); return MRT_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const uint32_t n = width * height;
+    running_mean_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>((const float4 *) acc_dev, (float4 *) mean_dev, n, pass, max_luminance);
+    CUDA_TRY(cudaGetLastError());
+    return MRT_OK;
+}
+
+// draw2 as a whole (main.cpp:193-243 with work_queue_dynamic, work_queue.cpp:158-166): `passes` one-sample launches
+// (samples sample_begin .. sample_begin + passes - 1 of the grid), each followed by the running-mean update; the mean is
+// left in the scene's image buffer and copied to rgba_host (w = number of passes).
+extern "C" int mrt_gpu_render_running_mean(MrtScene *s, const MrtRenderParams *p, float *rgba_host) {
+    if (!s || !p) { set_error("mrt_gpu_render_running_mean: null argument"); return MRT_E_INVALID; }
+    if (s->ext_acc) { set_error("mrt_gpu_render_running_mean: unbind the external accumulator first"); return MRT_E_STATE; }
+    uint32_t cx0 = p->crop_x0, cy0 = p->crop_y0, cx1 = p->crop_x1, cy1 = p->crop_y1;
+    if (!(cx0 | cy0 | cx1 | cy1)) { cx1 = p->width; cy1 = p->height; }
+    if (cx0 >= cx1 || cy0 >= cy1 || p->sample_begin >= p->sample_end) { set_error("mrt_gpu_render_running_mean: bad window or sample range"); return MRT_E_INVALID; }
+    const uint32_t w = cx1 - cx0, h = cy1 - cy0;
+    for (uint32_t pass = 0; p->sample_begin + pass < p->sample_end; pass++) {
+        MrtRenderParams one = *p;
+        one.sample_begin = p->sample_begin + pass;
+        one.sample_end = one.sample_begin + 1u;
+        one.flags = (p->flags & ~MRT_RENDER_ACCUMULATE) | (pass ? MRT_RENDER_CONTINUE : 0u);   // statistics run over all passes
+        int rc = mrt_gpu_render_async(s, &one);
+        if (rc) return rc;
+        if (pass == 0) { rc = ensure_final(s, (size_t) w * h); if (rc) return rc; }
+        rc = mrt_gpu_running_mean_update(s, s->last_acc, s->final_buf, w, h, pass, p->max_luminance);
+        if (rc) return rc;
+    }
+    s->final_is_running_mean = true;   // readback(finalize) / tonemap now deliver this image (until the next plain render)
+    if (rgba_host) {
+        CUDA_TRY(cudaMemcpyAsync(rgba_host, s->final_buf, (size_t) w * h * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
     return MRT_OK;
 }
 
@@ -826,10 +899,13 @@ extern "C" int mrt_gpu_tonemap(MrtScene *s, uint32_t *argb_host) {
     if (!s->rendered) { set_error("mrt_gpu_tonemap: nothing rendered yet"); return MRT_E_STATE; }
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t n = (size_t) s->last_w * s->last_h;
-    int rc = ensure_final(s, n);
-    if (rc) return rc;
-    rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
-    if (rc) return rc;
+    int rc = MRT_OK;
+    if (!s->final_is_running_mean) {
+        rc = ensure_final(s, n);
+        if (rc) return rc;
+        rc = mrt_gpu_finalize_device(s, s->last_acc, s->final_buf, s->last_w, s->last_h, s->last.max_luminance);
+        if (rc) return rc;
+    }
     rc = mrt_gpu_tonemap_device(s, s->final_buf, s->argb_buf, s->last_w, s->last_h);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(argb_host, s->argb_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));

@@ -19,7 +19,7 @@
 //
 // usage:
 //   mrt_ref render -scene S -width W -height H -samples N -depth D -seed X
-//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] [-lights all] -out file.bin
+//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] [-lights all] [-draw2 1] -out file.bin
 //                  (crop window: only those pixels of the W x H frame are traced; stream ids and u,v stay the
 //                   full frame's, so BASELINE.json's full-size configurations can be spot-checked in seconds)
 //   mrt_ref stock  <reference command line>  [-dump file.bin] [-dumpargb file.u32]   (final linear frame / its tone map)
@@ -298,6 +298,10 @@ static int cmd_render(int argc, char **argv) {
     std::vector<float> acc((size_t) CW * CH * 4, 0.0f);
     std::atomic<uint32> nextRow(y0);
     G_rayCounter = 0;
+    // -draw2 1: the pixel update of the reference's default worker, draw2 (main.cpp:214-231), instead of the plain sum:
+    // running mean over the samples in order, a non-finite sample replaced by the mean so far (0 for the first), and the
+    // luminance clamp applied after EVERY sample, feeding back into the mean.  Output: rgb = final mean, w = 1.
+    const bool draw2_mode = atoi(argval(argc, argv, "-draw2", "0")) != 0;
 
     uint64 t0 = MRT_GetTime();
     auto worker = [&]() {
@@ -307,7 +311,7 @@ static int cmd_render(int argc, char **argv) {
             for (uint32 x = x0; x < x1; x++) {
                 Vec3 color(0, 0, 0);
                 uint32 cnt = 0;
-                for (uint32 s = s0; s < s1; s++) {
+                for (uint32 s = s0; s < s1 && !draw2_mode; s++) {
                     // one private PCG32 stream per (pixel, sample)
                     Init_Thread_RNG(seed, ((uint64) y * W + x) * N + s);
                     float u = (x + sd[s].x) / (float) W;   // main.cpp:156-157
@@ -320,6 +324,24 @@ static int cmd_render(int argc, char **argv) {
                     }
                 }
                 float *o = &acc[((size_t) (y - y0) * CW + (x - x0)) * 4];
+                if (draw2_mode) {
+                    Vec3 mean(0.0f);
+                    for (uint32 s = s0; s < s1; s++) {
+                        Init_Thread_RNG(seed, ((uint64) y * W + x) * N + s);
+                        float u = (x + sd[s].x) / (float) W;
+                        float v = (y + sd[s].y) / (float) H;
+                        ray r = sc.camera->get_ray(u, v);
+                        Vec3 c = trace(r, *sc.objects, sc.biased_objects, 0);
+                        const uint32 sampleCount = s - s0;
+                        if (!isfinite(c.r) || !isfinite(c.g) || !isfinite(c.b)) c = sampleCount > 0 ? mean : Vec3(0.0f);   // main.cpp:214-219
+                        if (sampleCount > 0) c = mean + (c - mean) * (1.0f / (sampleCount + 1.0f));                         // main.cpp:221-224
+                        float lum = luminance(c);
+                        if (lum > p.maxLuminance) c = c * (p.maxLuminance / lum);                                           // main.cpp:226-229
+                        mean = c;
+                    }
+                    o[0] = mean.r; o[1] = mean.g; o[2] = mean.b; o[3] = 1.0f;
+                    continue;
+                }
                 o[0] = color.r; o[1] = color.g; o[2] = color.b; o[3] = (float) cnt;
             }
         }

@@ -430,3 +430,25 @@ def test_reduce_finalize_over_peer_memory(devices):
     assert res["n_bad"] == 0, res
     d = np.abs(((argb >> 8) & 255).astype(np.int32) - ((argb_one >> 8) & 255).astype(np.int32))
     assert d.max() <= 1
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,spp,maxlum", [(5, 96, 54, 16, 0.5), (0, 64, 64, 9, 1000.0)])
+def test_draw2_running_mean_matches_reference(scene, w, h, spp, maxlum):
+    """mrt_gpu_render_running_mean = the reference's default mode (draw2, main.cpp:193-243): one-sample passes, running mean, the
+    luminance clamp after every pass feeding back into the mean, a non-finite sample replaced by the mean so far.  Oracle:
+    `mrt_ref render -draw2 1` (the same pixel update around the reference's trace(), identical streams)."""
+    ref, _ = oracle_util.ref_render(scene, w, h, spp, draw2=True, maxlum=maxlum)
+    hs = api.HostScene(scene, w, h)
+    r = api.Renderer(hs, 0)
+    try:
+        mean = r.render_running_mean(w, h, spp, max_luminance=maxlum)
+        st = r.stats()
+        again = r.readback(finalize=True)           # the image buffer now IS the running mean
+    finally:
+        r.close(); hs.close()
+    assert st["paths"] == w * h * spp and st["mode"] == api.MODE_BINNED
+    np.testing.assert_array_equal(mean[..., 3], np.float32(spp))
+    np.testing.assert_array_equal(again, mean)
+    res = accfile.compare(mean[..., :3], ref[..., :3], rel=REL_TOL)
+    assert res["frac_ok"] >= MIN_FRAC, res

@@ -83,3 +83,33 @@ def test_libm_canonicalisation_is_a_small_change():
     assert identical > 0.95, identical
     res = accfile.compare(accfile.finalize(cr), accfile.finalize(host), rel=1e-4)
     assert res["frac_ok"] > 0.995, res
+
+
+@pytest.mark.skipif(not oracle_util.have_ref(), reason="oracle/_ref/mrt_ref not built")
+def test_draw2_running_mean_semantics():
+    """`mrt_ref render -draw2 1` = the reference's default worker's pixel update (draw2, main.cpp:214-231): running mean in sample
+    order, luminance clamp after EVERY sample feeding back into the mean.  Cross-check against a float32 numpy restatement fed
+    with the per-sample radiance of the same streams (one oracle render per sample), with a clamp low enough to fire often."""
+    from miniraytracer_b200 import accfile
+    scene, w, h, spp, maxlum = 5, 24, 13, 9, 0.15
+    got, _ = oracle_util.ref_render(scene, w, h, spp, draw2=True, maxlum=maxlum)
+    mean = np.zeros((h, w, 3), dtype=np.float32)
+    c709 = np.array([0.212655, 0.715158, 0.072187], dtype=np.float32)
+    clamped = 0
+    for s in range(spp):
+        one, _ = oracle_util.ref_render(scene, w, h, spp, s0=s, s1=s + 1)
+        finite = one[..., 3:4] > 0
+        c = np.where(finite, one[..., :3], mean if s else np.float32(0)).astype(np.float32)
+        if s:
+            c = (mean + (c - mean) * (np.float32(1.0) / np.float32(s + 1.0))).astype(np.float32)
+        prod = c * c709
+        lum = (prod[..., 0] + prod[..., 1]) + prod[..., 2]
+        over = lum > np.float32(maxlum)
+        clamped += int(over.sum())
+        with np.errstate(divide="ignore", invalid="ignore"):
+            k = (np.float32(maxlum) / lum).astype(np.float32)
+        mean = np.where(over[..., None], c * k[..., None], c).astype(np.float32)
+    assert clamped > 10
+    np.testing.assert_array_equal(got[..., :3], mean)
+    plain = accfile.finalize(oracle_util.ref_render(scene, w, h, spp)[0], maxlum)
+    assert np.abs(plain - mean).max() > 1e-3      # the per-pass clamp is NOT the same as clamping the final mean
