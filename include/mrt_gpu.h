@@ -68,7 +68,11 @@ typedef struct MrtHostScene MrtHostScene;
  * count 1 (scene.cpp:326-329, 456-459), so only the rect is importance-sampled.  OR-ing this flag into `scene` builds the list
  * with both (the sphere then goes through sphere::pdf_value / pdf_generate, sphere.cpp:63-79).  Default = the reference's count. */
 #define MRT_SCENE_ALL_LIGHTS 0x100u
-/* scene: the reference's enum scenes value (scene.h:6-17), optionally | MRT_SCENE_ALL_LIGHTS; aspect = width/height. */
+/* Cornell box (scene 5) only: two triangle_scene_objects (triangle.cpp:5-175 -- a class no stock scene instantiates) appended to
+ * the object list, one with a face normal, one with vertex normals; exists so that the class has a parity test. */
+#define MRT_SCENE_EXTRA_TRIANGLES 0x200u
+/* scene: the reference's enum scenes value (scene.h:6-17), optionally | MRT_SCENE_ALL_LIGHTS | MRT_SCENE_EXTRA_TRIANGLES;
+ * aspect = width/height. */
 int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHostScene **out);
 /* Flattened description (pointers stay valid until mrt_scene_free). */
 const MrtSceneDesc *mrt_scene_desc(const MrtHostScene *s);

@@ -76,6 +76,7 @@ enum MrtRefType {
     MRT_T_ROTATE_Y = 8,
     MRT_T_VOLUME = 9,
     MRT_T_TRILEAF = 10,
+    MRT_T_TRI = 11, /* triangle_scene_object: one triangle of tri[] / trin[] as a list child (triangle.cpp:5-175) */
     MRT_T_END = 15 /* list terminator */
 };
 #define MRT_REF(type, index) ((uint32_t) (((uint32_t) (type) << 24) | ((uint32_t) (index) & 0xFFFFFFu)))
@@ -106,7 +107,8 @@ enum MrtMatKind {
 #define MRT_FEAT_SPHERES 256u     /* the scene has spheres */
 #define MRT_FEAT_TRIS 512u        /* triangle leaves (pod_bvh) */
 #define MRT_FEAT_LEAF_LISTS 1024u /* some tree leaf is an object_list (bvh_node leaves) */
-#define MRT_FEAT_ALL 2047u
+#define MRT_FEAT_TRI_OBJECT 2048u /* lone triangles as scene objects (triangle_scene_object) */
+#define MRT_FEAT_ALL 4095u
 
 enum MrtTexKind { MRT_X_COLOR = 0, MRT_X_CHECKER = 1, MRT_X_PERLIN = 2, MRT_X_IMAGE = 3 };
 

@@ -83,6 +83,7 @@ class RenderStats(C.Structure):
 
 MRT_RENDER_ACCUMULATE = 1
 MRT_RENDER_CONTINUE = 2
+SCENE_EXTRA_TRIANGLES = 0x200   # MRT_SCENE_EXTRA_TRIANGLES: two triangle_scene_objects in the Cornell box
 SCENE_ALL_LIGHTS = 0x100   # MRT_SCENE_ALL_LIGHTS: light list with both allocated entries (ceiling light + glass sphere)
 DEFAULT_SEED = 11350390909718046443  # main.cpp:302
 

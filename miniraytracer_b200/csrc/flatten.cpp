@@ -93,7 +93,7 @@ struct Flattener {
     // a volume boundary is therefore wrapped into a box-less one-element list -- same result: the list
     // passes (tmin, tmax) through and reports its only child's hit (scene_object.h:79-103).
     std::map<uint32_t, uint32_t> wrap_memo;
-    static bool is_prim(uint32_t ref) { return MRT_REF_TYPE(ref) <= MRT_T_RECT_YZ; }
+    static bool is_prim(uint32_t ref) { return MRT_REF_TYPE(ref) <= MRT_T_RECT_YZ || MRT_REF_TYPE(ref) == MRT_T_TRI; }
     uint32_t wrap(uint32_t ref) {
         if (!is_prim(ref)) return ref;
         auto it = wrap_memo.find(ref);
@@ -110,7 +110,7 @@ struct Flattener {
     }
     bool node_is_prim(int id) const {
         NodeKind k = g.nodes[id].kind;
-        return k == NodeKind::Sphere || k == NodeKind::RectXY || k == NodeKind::RectXZ || k == NodeKind::RectYZ;
+        return k == NodeKind::Sphere || k == NodeKind::RectXY || k == NodeKind::RectXZ || k == NodeKind::RectYZ || k == NodeKind::Triangle;
     }
 
     // ---- wide BVH nodes (children's boxes stored in the parent, see mrt_types.h)
@@ -208,6 +208,19 @@ struct Flattener {
             o.rect.push_back(f4(n.k, n.sign, ubits(m), 0));
             uint32_t type = n.kind == NodeKind::RectXY ? MRT_T_RECT_XY : (n.kind == NodeKind::RectXZ ? MRT_T_RECT_XZ : MRT_T_RECT_YZ);
             ref = MRT_REF(type, i);
+            break;
+        }
+        case NodeKind::Triangle: {   // triangle_scene_object: one record in the triangle tables, referenced as a primitive
+            uint32_t i = (uint32_t) o.tri.size() / 3;
+            uint32_t m = mat(n.mat);
+            const Triangle &t = n.tri;
+            o.tri.push_back(f4(t.m.x, t.m.y, t.m.z, ubits(m)));
+            o.tri.push_back(f4(t.u.x, t.u.y, t.u.z, 0));
+            o.tri.push_back(f4(t.v.x, t.v.y, t.v.z, 0));
+            o.trin.push_back(f4(t.mn.x, t.mn.y, t.mn.z, 0));
+            o.trin.push_back(f4(t.un.x, t.un.y, t.un.z, 0));
+            o.trin.push_back(f4(t.vn.x, t.vn.y, t.vn.z, 0));
+            ref = MRT_REF(MRT_T_TRI, i);
             break;
         }
         case NodeKind::Box:   // box::hit forwards to its rect list (box.h:23-25)
@@ -396,6 +409,7 @@ bool validate_scene_desc(const MrtSceneDesc &d, std::string *err, uint32_t *stac
         case MRT_T_ROTATE_Y: return i < d.n_rot;
         case MRT_T_VOLUME: return i < d.n_vol;
         case MRT_T_TRILEAF: return i < d.n_trileaf;
+        case MRT_T_TRI: return i < d.n_tri;
         default: return false;
         }
     };
@@ -463,7 +477,7 @@ bool validate_scene_desc(const MrtSceneDesc &d, std::string *err, uint32_t *stac
         case MRT_T_LIST: {
             uint32_t m = 0;
             for (uint32_t ci = u(d.list[2 * i].w); MRT_REF_TYPE(d.child[ci]) != MRT_T_END; ci++)
-                if (MRT_REF_TYPE(d.child[ci]) > MRT_T_RECT_YZ) m = std::max(m, self(d.child[ci], level + 1, self));
+                if (MRT_REF_TYPE(d.child[ci]) > MRT_T_RECT_YZ && MRT_REF_TYPE(d.child[ci]) != MRT_T_TRI) m = std::max(m, self(d.child[ci], level + 1, self));
             return 1 + m;
         }
         case MRT_T_BVH: return coop ? 0u : self(u(d.bvh[2 * i].w), level + 1, self);
@@ -511,7 +525,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &op
     }
     const size_t lim = 0xFFFFFFu;
     if (o.sphere.size() / 3 > lim || o.rect.size() / 2 > lim || o.list.size() / 2 > lim || o.bvh.size() / 2 > lim ||
-        o.node2.size() / 4 > lim || o.trileaf.size() / 2 > lim || o.xlate.size() / 3 > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
+        o.node2.size() / 4 > lim || o.trileaf.size() / 2 > lim || o.tri.size() / 3 > lim || o.xlate.size() / 3 > lim || o.rot.size() / 3 > lim || o.vol.size() > lim)
         fl.fail("too many objects of one type for a 24-bit index");
     if (o.child.size() > 0x0FFFFFFFu) fl.fail("child table too large");
     if (!fl.ok) return false;
@@ -557,6 +571,7 @@ bool flatten_scene(const SceneGraph &g, FlatScene *out, const FlattenOptions &op
         for (uint32_t l : o.lights) if (MRT_REF_TYPE(l) != MRT_T_RECT_XZ) f |= MRT_FEAT_LIGHT_SPHERE;
         if (!o.sphere.empty()) f |= MRT_FEAT_SPHERES;
         if (!o.trileaf.empty()) f |= MRT_FEAT_TRIS;
+        for (const Node &n : g.nodes) if (n.kind == NodeKind::Triangle) f |= MRT_FEAT_TRI_OBJECT;
         for (size_t i = 0; i < o.node2.size(); i += 4) {   // kinds of the two children, see fill_node2
             const uint32_t fl = ubits_of(o.node2[i + 2].w);
             if (((fl >> 2) & 3u) == 1u || ((fl >> 4) & 3u) == 1u) f |= MRT_FEAT_LEAF_LISTS;

@@ -147,7 +147,7 @@ struct MrtHostScene {
 extern "C" int mrt_scene_create(uint32_t scene, float aspect, const char *asset_dir, MrtHostScene **out) {
     if (!out) { set_error("mrt_scene_create: null argument"); return MRT_E_INVALID; }
     *out = nullptr;
-    if ((scene & 0xFFu) > 8 || (scene & ~(0xFFu | MRT_SCENE_ALL_LIGHTS))) { set_error("mrt_scene_create: scene must be in [0, 8] (| MRT_SCENE_ALL_LIGHTS)"); return MRT_E_INVALID; }
+    if ((scene & 0xFFu) > 8 || (scene & ~(0xFFu | MRT_SCENE_ALL_LIGHTS | MRT_SCENE_EXTRA_TRIANGLES))) { set_error("mrt_scene_create: scene must be in [0, 8] (| MRT_SCENE_ALL_LIGHTS)"); return MRT_E_INVALID; }
     MrtHostScene *s = new (std::nothrow) MrtHostScene();
     if (!s) { set_error("out of memory"); return MRT_E_INVALID; }
     if (!build_scene(s->graph, scene, aspect, asset_dir ? asset_dir : "assets")) {

@@ -590,7 +590,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     // measured (profiles/r1_notes.md): tree scenes want 96 registers; list scenes 64 registers / 8 blocks in modes
     // W and P, but 80 registers / 6 blocks in mode B (fewer resident warps thrash the instruction cache less)
     int minb = tn.min_blocks ? (int) tn.min_blocks : (s->has_trees ? 5 : (binned ? 6 : 8));
-    const Variant *variant = tn.variant_all ? pick_variant(MRT_FEAT_ALL) : pick_variant(s->features);
+    const Variant *variant = tn.variant_all ? pick_variant(s->features | MRT_VARIANT_STOCK) : pick_variant(s->features);
     // BVH trees: warp-cooperative traversal (coop_tree.cuh) in mode B where the scene's trees qualify
     const bool coop_ok = binned && s->has_trees && s->stack_words_coop != 0u && (variant->mask & MRT_FEAT_TREES);
     if (tn.coop_trees == 2u && !coop_ok) { set_error("mrt_gpu_render_async: cooperative tree traversal needs mode B and qualifying trees"); return MRT_E_INVALID; }

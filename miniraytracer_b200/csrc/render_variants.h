@@ -22,6 +22,9 @@ namespace mrt {
 // and the kernel is 57 % SLOWER on scene 0 (measured, profiles/r2_notes.md) -- a code-generation accident, kept on the good side
 #define MRT_VARIANT_TREES_TEX (MRT_FEAT_TREES | MRT_FEAT_TRIS | MRT_FEAT_LEAF_LISTS | MRT_FEAT_SPHERES | MRT_FEAT_METAL | MRT_FEAT_DIELECTRIC | MRT_FEAT_TEX | MRT_FEAT_MOVING)
 
+// everything the nine stock scenes can contain (no triangle_scene_object: no stock scene has one)
+#define MRT_VARIANT_STOCK (MRT_FEAT_ALL & ~MRT_FEAT_TRI_OBJECT)
+
 const void *variant_cornell(int kind, int minb);
 const void *variant_cornell_vol(int kind, int minb);
 const void *variant_lists(int kind, int minb);
@@ -29,6 +32,7 @@ const void *variant_lists_vol(int kind, int minb);
 const void *variant_trees(int kind, int minb);
 const void *variant_trees_tex(int kind, int minb);
 const void *variant_all(int kind, int minb);
+const void *variant_full(int kind, int minb);
 
 struct Variant {
     uint32_t mask;
@@ -43,7 +47,8 @@ inline const Variant *pick_variant(uint32_t scene_features) {
         {MRT_VARIANT_LISTS_VOL, variant_lists_vol, "lists+volumes"},
         {MRT_VARIANT_TREES, variant_trees, "trees"},
         {MRT_VARIANT_TREES_TEX, variant_trees_tex, "trees+textures"},
-        {MRT_FEAT_ALL, variant_all, "all"},
+        {MRT_VARIANT_STOCK, variant_all, "all stock features"},
+        {MRT_FEAT_ALL, variant_full, "all"},
     };
     if (scene_features == 0) scene_features = MRT_FEAT_ALL;   // unknown: keep everything
     for (const Variant &v : table)

@@ -64,6 +64,11 @@ static void dump_obj(const SceneGraph &g, FILE *f, int id, int d) {
         pf(f, "a0", n.a0); pf(f, "a1", n.a1); pf(f, "b0", n.b0); pf(f, "b1", n.b1); pf(f, "k", n.k); pf(f, "sign", n.sign);
         fprintf(f, " mat="); dump_mat(g, f, n.mat); fprintf(f, "\n");
         break;
+    case NodeKind::Triangle:
+        ind(f, d); fprintf(f, "triangle_object");
+        pv(f, "m", n.tri.m); pv(f, "u", n.tri.u); pv(f, "v", n.tri.v); pv(f, "mn", n.tri.mn); pv(f, "un", n.tri.un); pv(f, "vn", n.tri.vn);
+        fprintf(f, " mat="); dump_mat(g, f, n.mat); fprintf(f, "\n");
+        break;
     case NodeKind::Box:
         ind(f, d); fprintf(f, "box"); pv(f, "min", n.box.min); pv(f, "max", n.box.max); fprintf(f, "\n");
         dump_obj(g, f, n.child, d + 1);

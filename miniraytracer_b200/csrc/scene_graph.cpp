@@ -124,6 +124,24 @@ static int make_rect(SceneGraph &g, NodeKind kind, float a0, float a1, float b0,
 }
 int SceneGraph::xy_rect(float x0, float x1, float y0, float y1, float z, int mat) { return make_rect(*this, NodeKind::RectXY, x0, x1, y0, y1, z, mat); }
 int SceneGraph::xz_rect(float x0, float x1, float z0, float z1, float y, int mat) { return make_rect(*this, NodeKind::RectXZ, x0, x1, z0, z1, y, mat); }
+int SceneGraph::triangle(H3 a, H3 b, H3 c, int mat) {   // triangle.cpp:5-17: m, u = b - a, v = c - a, one face normal
+    Node n;
+    n.kind = NodeKind::Triangle;
+    n.mat = mat;
+    n.tri.m = a; n.tri.u = b - a; n.tri.v = c - a;
+    n.tri.mn = n.tri.un = n.tri.vn = hnormalize(hcross(n.tri.u, n.tri.v));
+    nodes.push_back(n);
+    return (int) nodes.size() - 1;
+}
+int SceneGraph::triangle(H3 a, H3 b, H3 c, H3 an, H3 bn, H3 cn, int mat) {   // triangle.cpp:19-35
+    Node n;
+    n.kind = NodeKind::Triangle;
+    n.mat = mat;
+    n.tri.m = a; n.tri.u = b - a; n.tri.v = c - a;
+    n.tri.mn = an; n.tri.un = bn; n.tri.vn = cn;
+    nodes.push_back(n);
+    return (int) nodes.size() - 1;
+}
 int SceneGraph::yz_rect(float y0, float y1, float z0, float z1, float x, int mat) { return make_rect(*this, NodeKind::RectYZ, y0, y1, z0, z1, x, mat); }
 
 int SceneGraph::box(H3 mn, H3 mx, int mat) {   // box.h:12-21
@@ -170,6 +188,11 @@ bool SceneGraph::bounding_box(int id, float t0, float t1, Aabb *out) const {
     case NodeKind::RotateY: *out = n.box; return n.has_box;
     case NodeKind::Volume: return bounding_box(n.child, t0, t1, out);
     case NodeKind::PodBvh: *out = meshes[n.mesh].nodes[0].box; return true;
+    case NodeKind::Triangle: {   // triangle.cpp:37-45: vmin / vmax of the three corners
+        const H3 a = n.tri.m, b = n.tri.m + n.tri.u, c = n.tri.m + n.tri.v;
+        *out = Aabb{hmin(hmin(a, b), c), hmax(hmax(a, b), c)};
+        return true;
+    }
     }
     return false;
 }

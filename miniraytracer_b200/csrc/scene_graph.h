@@ -47,7 +47,7 @@ struct HostRng {
     H3 in_sphere();
 };
 
-enum class NodeKind : uint8_t { Sphere, RectXY, RectXZ, RectYZ, Box, List, Bvh, Translate, RotateY, Volume, PodBvh };
+enum class NodeKind : uint8_t { Sphere, RectXY, RectXZ, RectYZ, Box, List, Bvh, Translate, RotateY, Volume, PodBvh, Triangle };
 enum class MatKind : uint8_t { Lambertian, Isotropic, Metal, Dielectric, Light };
 enum class TexKind : uint8_t { Color, Checker, Perlin, Image };
 
@@ -101,6 +101,7 @@ struct Node {
     float sin_theta = 0, cos_theta = 0;
     float density = 0;           // volume (mat = isotropic phase function)
     int mesh = -1;               // pod_bvh
+    Triangle tri;                // triangle_scene_object (triangle.cpp:5-175): a lone triangle as a scene object
 };
 
 struct Camera {   // camera.h
@@ -136,6 +137,8 @@ struct SceneGraph {
 
     // objects (constructors of the reference classes)
     int sphere(H3 c0, float r, int mat, H3 c1 = H3(0, 0, 0), float t0 = 0.0f, float t1 = 0.0f);
+    int triangle(H3 a, H3 b, H3 c, int mat);                                   // triangle.cpp:5-17 (face normal)
+    int triangle(H3 a, H3 b, H3 c, H3 an, H3 bn, H3 cn, int mat);             // triangle.cpp:19-35 (vertex normals)
     int xy_rect(float x0, float x1, float y0, float y1, float z, int mat);
     int xz_rect(float x0, float x1, float z0, float z1, float y, int mat);
     int yz_rect(float y0, float y1, float z0, float z1, float x, int mat);

@@ -150,7 +150,7 @@ static bool earth(SceneGraph &g, float aspect, const std::string &assets) {   //
     return true;
 }
 
-static bool cornell_box(SceneGraph &g, float aspect, bool all_lights) {   // scene.cpp:283-332
+static bool cornell_box(SceneGraph &g, float aspect, bool all_lights, bool extra_triangles) {   // scene.cpp:283-332
     g.camera = cornell_camera(aspect, 0.0f);
     int red = g.lambertian(g.color_tex(H3(0.65f, 0.055f, 0.06f)));
     int white = g.lambertian(g.color_tex(H3(0.73f, 0.73f, 0.73f)));
@@ -168,6 +168,13 @@ static bool cornell_box(SceneGraph &g, float aspect, bool all_lights) {   // sce
     l.push_back(g.translate(g.rotate_y(g.box(H3(0, 0, 0), H3(165, 330, 165), white), 15), H3(265, 0, 295)));
     int s = g.sphere(H3(190, 90, 190), 90, glass);
     l.push_back(s);
+    if (extra_triangles) {
+        // MRT_SCENE_EXTRA_TRIANGLES: two triangle_scene_objects (triangle.cpp:5-175; no stock scene uses the class) appended to the
+        // object list -- one with a face normal, one with vertex normals; the oracle harness appends the same two (`-extra triangles`)
+        l.push_back(g.triangle(H3(100, 300, 250), H3(400, 320, 300), H3(250, 520, 420), red));
+        l.push_back(g.triangle(H3(420, 60, 120), H3(520, 60, 260), H3(470, 260, 180), H3(0, 0, -1), H3(-0.6f, 0, -0.8f), H3(0, 0.6f, -0.8f),
+                               g.metal(g.color_tex(H3(0.8f, 0.85f, 0.88f)), 0.9f)));
+    }
     g.objects = g.list(l, 0.0f, 1.0f);
     // the array holds {light, sphere} but the list is built with count 1 (scene.cpp:326-329); MRT_SCENE_ALL_LIGHTS uses both
     g.biased = all_lights ? g.list(std::vector<int>{lrect, s}, 0.0f, 1.0f) : g.list(std::vector<int>{lrect}, 0.0f, 1.0f);
@@ -286,6 +293,7 @@ static bool triangles(SceneGraph &g, float aspect, const std::string &assets) { 
 bool build_scene(SceneGraph &g, uint32_t scene_and_flags, float aspect, const std::string &asset_dir) {
     const uint32_t scene = scene_and_flags & 0xFFu;
     const bool all_lights = (scene_and_flags & MRT_SCENE_ALL_LIGHTS) != 0;
+    const bool extra_triangles = (scene_and_flags & MRT_SCENE_EXTRA_TRIANGLES) != 0;
     HostRng rng;
     rng.seed(11350390909718046443uLL, 6305599193148252115uLL);   // main.cpp:302
     g.sky = scene < 5;                                            // main.cpp:110
@@ -295,7 +303,7 @@ bool build_scene(SceneGraph &g, uint32_t scene_and_flags, float aspect, const st
     case 2: return two_spheres(g, aspect);
     case 3: return spheres_perlin(g, aspect);
     case 4: return earth(g, aspect, asset_dir);
-    case 5: return cornell_box(g, aspect, all_lights);
+    case 5: return cornell_box(g, aspect, all_lights, extra_triangles);
     case 6: return cornell_smoke(g, aspect);
     case 7: return book2_final(g, rng, aspect, asset_dir, all_lights);
     case 8: return triangles(g, aspect, asset_dir);

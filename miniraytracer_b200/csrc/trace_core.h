@@ -627,6 +627,9 @@ MRT_HD bool isect_run(const uint32_t feat, const SceneView &sc, Ray &ray, Isect 
                     } else if (ctype <= MRT_T_RECT_YZ) {
                         if (cnt) cnt->rect++;
                         if (hit_rect(feat, sc, ctype - MRT_T_RECT_XY, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
+                    } else if (MRT_HAS(feat, MRT_FEAT_TRI_OBJECT) && ctype == MRT_T_TRI) {   // triangle_scene_object::hit (triangle.cpp:49-91) = triangle::hit
+                        if (cnt) cnt->tri++;
+                        if (hit_triangle(sc, MRT_REF_INDEX(c), ray, tmin, tmax, !probe, rec)) { found = true; tmax = rec.t; }
                     } else {
                         st.push(MRT_FRAME(MRT_F_LIST, ci) | (found ? (1u << 28) : 0u));
                         cur = c;

@@ -21,6 +21,7 @@ Patch list:
      compiler independent: pcg.cpp:73,115  rect.cpp:105
      scene.cpp:78,86,90,156,164,169,450.
   P9 access only: `public:` added to pod_bvh (triangle.h:58) so the scene dump can read it.
+  P10 access only: `public:` added to triangle_scene_object (triangle.h:326) for the same reason.
 No arithmetic is changed by any source patch.  Separately, at LINK time, the six libm functions the path
 calls are bound to correctly rounded versions (oracle/cr_libm.cpp; rationale in
 miniraytracer_b200/csrc/mrt_libm.h); MRT_ORACLE_LIBM=host restores the host libm's own.
@@ -76,6 +77,9 @@ patch("triangle.h", '#include "scene_object.h"', '#include <cstring>\n#include "
 # dump of the harness needs to read them.
 patch("triangle.h", "class pod_bvh final : public scene_object {",
       "class pod_bvh final : public scene_object {\npublic:")
+# P10 access only: the same for triangle_scene_object's members (triangle.h:326-334)
+patch("triangle.h", "class triangle_scene_object final : public scene_object {",
+      "class triangle_scene_object final : public scene_object {\npublic:")
 
 # P8 -- explicit left->right sequencing of RNG draws
 patch("pcg.cpp",

@@ -19,7 +19,7 @@
 //
 // usage:
 //   mrt_ref render -scene S -width W -height H -samples N -depth D -seed X
-//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] [-lights all] [-draw2 1] -out file.bin
+//                  [-s0 a -s1 b] [-x0 a -x1 b -y0 c -y1 d] [-threads T] [-maxlum L] [-lights all] [-extra triangles] [-draw2 1] -out file.bin
 //                  (crop window: only those pixels of the W x H frame are traced; stream ids and u,v stay the
 //                   full frame's, so BASELINE.json's full-size configurations can be spot-checked in seconds)
 //   mrt_ref stock  <reference command line>  [-dump file.bin] [-dumpargb file.u32]   (final linear frame / its tone map)
@@ -199,6 +199,10 @@ static void dump_obj(FILE *f, const scene_object *o, int d) {
         dump_obj(f, v->boundary, d + 1);
     } else if (auto p = dynamic_cast<const pod_bvh<triangle> *>(o)) {
         dump_podbvh(f, p, d);
+    } else if (auto t = dynamic_cast<const triangle_scene_object *>(o)) {
+        ind(f, d); fprintf(f, "triangle_object");
+        pv(f, "m", t->m); pv(f, "u", t->u); pv(f, "v", t->v); pv(f, "mn", t->mn); pv(f, "un", t->un); pv(f, "vn", t->vn);
+        fprintf(f, " mat="); dump_mat(f, t->mat_ptr); fprintf(f, "\n");
     } else {
         ind(f, d); fprintf(f, "unknown-object\n");
     }
@@ -231,6 +235,22 @@ static scene build_scene(uint32 sceneSelect, uint32 W, uint32 H) {
     // main.cpp:302-309
     Init_Thread_RNG(11350390909718046443uLL, 6305599193148252115uLL);
     return select_scene((scenes) sceneSelect, float(W) / float(H));
+}
+
+// "-extra triangles" (Cornell box only): appends two triangle_scene_objects (triangle.cpp:5-175 -- a class of the reference that
+// none of its scenes instantiates) to the scene's object list, one through each constructor, so that the class has an oracle.
+// The reference's object_list is rebuilt with the longer array (its constructor also recomputes the list's box).
+static void add_extra_triangles(scene &sc) {
+    auto *old = (object_list<scene_object> *) sc.objects;
+    const size_t n = old->count;
+    scene_object **list = new scene_object *[n + 2];
+    for (size_t i = 0; i < n; i++) list[i] = old->list[i];
+    material *red = new lambertian(new color_tex(Vec3(0.65f, 0.055f, 0.06f)));
+    material *alu = new metal(new color_tex(Vec3(0.8f, 0.85f, 0.88f)), 0.9f);
+    list[n] = new triangle_scene_object(Vec3(100, 300, 250), Vec3(400, 320, 300), Vec3(250, 520, 420), red);
+    list[n + 1] = new triangle_scene_object(Vec3(420, 60, 120), Vec3(520, 60, 260), Vec3(470, 260, 180), Vec3(0, 0, -1), Vec3(-0.6f, 0, -0.8f),
+                                            Vec3(0, 0.6f, -0.8f), alu);
+    sc.objects = new object_list<scene_object>(list, n + 2, 0.0f, 1.0f);
 }
 
 struct FileHeader {
@@ -268,6 +288,7 @@ static int cmd_render(int argc, char **argv) {
     *getParams() = p;
 
     scene sc = build_scene(p.sceneSelect, W, H);
+    if (!strcmp(argval(argc, argv, "-extra", "none"), "triangles") && p.sceneSelect == 5) add_extra_triangles(sc);
     if (!strcmp(argval(argc, argv, "-lights", "ref"), "all") && sc.biased_objects) {
         // The Cornell box and the final scene allocate a light list of TWO objects (ceiling light, glass sphere) but pass
         // count 1 (scene.cpp:326-329, 456-459).  "-lights all" uses both, so that sphere::pdf_value / pdf_generate
@@ -432,6 +453,7 @@ static int cmd_dump_scene(int argc, char **argv) {
     const char *out = argval(argc, argv, "-out", nullptr);
     MRT_headless_quiet = true;
     scene sc = build_scene(sel, W, H);
+    if (!strcmp(argval(argc, argv, "-extra", "none"), "triangles") && sel == 5) add_extra_triangles(sc);
     if (!strcmp(argval(argc, argv, "-lights", "ref"), "all") && sc.biased_objects && (sel == 5 || sel == 7))
         ((object_list<scene_object> *) sc.biased_objects)->count = 2;   // see cmd_render
     FILE *f = out ? fopen(out, "w") : stdout;

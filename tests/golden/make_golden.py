@@ -31,6 +31,10 @@ if __name__ == "__main__":
         acc, meta = oracle_util.ref_render(scene, W, H, 16, DEPTH, all_lights=True)
         np.savez_compressed(os.path.join(HERE, f"golden_all_lights_scene{scene}.npz"), acc=acc, scene=scene, width=W, height=H,
                             spp=16, depth=DEPTH, seed=np.uint64(oracle_util.DEFAULT_SEED), rays=np.uint64(meta["rays"]))
+    # Cornell box + two triangle_scene_objects (`-extra triangles`): the lone-triangle class (triangle.cpp:5-175)
+    acc, meta = oracle_util.ref_render(5, W, H, 16, DEPTH, extra_triangles=True)
+    np.savez_compressed(os.path.join(HERE, "golden_extra_triangles_scene5.npz"), acc=acc, scene=5, width=W, height=H, spp=16, depth=DEPTH,
+                        seed=np.uint64(oracle_util.DEFAULT_SEED), rays=np.uint64(meta["rays"]))
     kat = oracle_util.ref_run(["kat"]).stdout
     open(os.path.join(HERE, "kat.txt"), "w").write(kat)
     # scene dumps printed by the reference + matching renders, used to test oracle/mrt_oracle.c without the reference binary

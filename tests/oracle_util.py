@@ -34,27 +34,28 @@ def ref_run(args, **kw):
     return subprocess.run([REF_BIN] + [str(a) for a in args], cwd=RUN_DIR, check=True, capture_output=True, text=True, **kw)
 
 
-def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0, crop=None, all_lights=False, host_libm=False, draw2=False, maxlum=None):
+def ref_render(scene, width, height, spp, depth=32, seed=DEFAULT_SEED, s0=0, s1=0, threads=0, crop=None, all_lights=False, host_libm=False, draw2=False, maxlum=None, extra_triangles=False):
     """Oracle render with per-(pixel, sample) RNG streams; returns (acc[h,w,4], meta). Cached in /tmp.
     crop = (x0, y0, x1, y1): only that window of the frame (stream ids and u,v stay the full frame's)."""
     from miniraytracer_b200.accfile import read_acc
     os.makedirs(CACHE, exist_ok=True)
     st = os.stat(REF_BIN)
-    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{crop}-{all_lights}-{host_libm}-{draw2}-{maxlum}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
+    key = hashlib.sha1(f"{scene}-{width}-{height}-{spp}-{depth}-{seed}-{s0}-{s1}-{crop}-{all_lights}-{host_libm}-{draw2}-{maxlum}-{extra_triangles}-{st.st_size}-{int(st.st_mtime)}".encode()).hexdigest()[:16]
     path = os.path.join(CACHE, f"ref_{key}.bin")
     if not os.path.exists(path):
         tmp = path + f".{os.getpid()}.tmp"
         ref_run(["render", "-scene", scene, "-width", width, "-height", height, "-samples", spp, "-depth", depth,
                  "-seed", seed, "-s0", s0, "-s1", s1, "-threads", threads, "-out", tmp] +
                 (["-x0", crop[0], "-y0", crop[1], "-x1", crop[2], "-y1", crop[3]] if crop else []) + (["-lights", "all"] if all_lights else []) +
-                (["-draw2", 1] if draw2 else []) + (["-maxlum", maxlum] if maxlum is not None else []),
+                (["-draw2", 1] if draw2 else []) + (["-extra", "triangles"] if extra_triangles else []) + (["-maxlum", maxlum] if maxlum is not None else []),
                 **({"env": dict(os.environ, MRT_ORACLE_LIBM="host")} if host_libm else {}))   # host: the box's own libm instead of the canonical one
         os.replace(tmp, path)
     return read_acc(path)
 
 
-def ref_dump_scene(scene, width, height, out, all_lights=False):
-    ref_run(["dump-scene", "-scene", scene, "-width", width, "-height", height, "-out", out] + (["-lights", "all"] if all_lights else []))
+def ref_dump_scene(scene, width, height, out, all_lights=False, extra_triangles=False):
+    ref_run(["dump-scene", "-scene", scene, "-width", width, "-height", height, "-out", out] + (["-lights", "all"] if all_lights else []) +
+            (["-extra", "triangles"] if extra_triangles else []))
 
 
 def build_emul():

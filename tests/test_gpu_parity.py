@@ -452,3 +452,12 @@ def test_draw2_running_mean_matches_reference(scene, w, h, spp, maxlum):
     np.testing.assert_array_equal(again, mean)
     res = accfile.compare(mean[..., :3], ref[..., :3], rel=REL_TOL)
     assert res["frac_ok"] >= MIN_FRAC, res
+
+
+def test_triangle_scene_object_golden():
+    """triangle_scene_object (triangle.cpp:5-175, used by no stock scene): two lone triangles in the Cornell box
+    (MRT_SCENE_EXTRA_TRIANGLES; oracle `-extra triangles`) against the reference; runs the everything-compiled-in kernel variant."""
+    g = np.load(os.path.join(GOLDEN, "golden_extra_triangles_scene5.npz"))
+    acc, st = _gpu_render(5 | api.SCENE_EXTRA_TRIANGLES, int(g["width"]), int(g["height"]), int(g["spp"]), int(g["depth"]))
+    _check(acc, g["acc"], int(g["rays"]), st)
+    assert int(st["rays"]) == int(g["rays"])

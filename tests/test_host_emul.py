@@ -99,3 +99,18 @@ def test_sphere_light_importance_sampling(emul_bin, scene, w, h, spp):
     np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
     res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
     assert res["n_bad"] == 0, res
+
+
+@needs_ref
+def test_triangle_scene_object(emul_bin):
+    """triangle_scene_object (triangle.cpp:5-175): a lone triangle as a scene object -- a class of the reference that none of its
+    scenes uses.  MRT_SCENE_EXTRA_TRIANGLES / the harness's `-extra triangles` put two of them (face normal, vertex normals) into
+    the Cornell box on both sides."""
+    ref, rmeta = oracle_util.ref_render(5, 96, 54, 16, extra_triangles=True)
+    stock, smeta = oracle_util.ref_render(5, 96, 54, 16)
+    assert rmeta["rays"] != smeta["rays"]
+    acc, meta = oracle_util.emul_render(emul_bin, 5 | 0x200, 96, 54, 16)
+    assert meta["rays"] == rmeta["rays"] and meta["counters"]["tri"] > 0
+    np.testing.assert_array_equal(acc[..., 3], ref[..., 3])
+    res = accfile.compare(accfile.finalize(acc), accfile.finalize(ref), rel=1e-5)
+    assert res["n_bad"] == 0, res

@@ -29,6 +29,23 @@ def test_scene_dump_identical(scene, size, tmp_path):
     assert a == b
 
 
+@needs_ref
+@pytest.mark.parametrize("flags,kw", [(api.SCENE_EXTRA_TRIANGLES, dict(extra_triangles=True))])
+def test_scene_dump_identical_with_options(flags, kw, tmp_path):
+    """The opt-in scene variant with two triangle_scene_objects (triangle.cpp:5-175) in the Cornell box against the reference's
+    graph built the same way by the oracle harness.  (MRT_SCENE_ALL_LIGHTS is not compared as a dump: the harness only raises
+    the count of the reference's light list, whose stored box -- unused by the pdfs -- then still covers one object.)"""
+    ref, mine = tmp_path / "ref.txt", tmp_path / "mine.txt"
+    oracle_util.ref_dump_scene(5, 640, 360, str(ref), **kw)
+    hs = api.HostScene(5 | flags, 640, 360)
+    hs.dump(mine)
+    feats = hs.desc.contents.features
+    hs.close()
+    assert ref.read_text() == mine.read_text()
+    if flags == api.SCENE_EXTRA_TRIANGLES:
+        assert "triangle_object" in mine.read_text() and feats & 2048      # MRT_FEAT_TRI_OBJECT
+
+
 def test_perlin_tables_match_reference():
     # texture.cpp:167-203 tables, built from the raw global generator state (pcg.cpp:40)
     lines = open(os.path.join(GOLDEN, "kat.txt")).read().splitlines()
