@@ -11,6 +11,7 @@ from miniraytracer_b200 import api  # noqa: E402
 
 CASES = {
     "C2n8": (5, 1920, 1080, 128), "C3n8": (6, 1920, 1080, 128), "C4n8": (7, 1920, 1080, 512), "C5n8": (8, 1920, 1080, 256),   # the per-GPU share of an 8-GPU run
+    "N_C4": (7, 1920, 1080, 64), "N_C5": (8, 3840, 2160, 16), "N_C3": (6, 1920, 1080, 64),   # bench resolution, few samples: ncu captures
     "C1": (0, 500, 500, 16), "C1hi": (0, 500, 500, 1024), "C2": (5, 960, 540, 1024), "C2full": (5, 1920, 1080, 1024),
     "C3": (6, 960, 540, 1024), "P_C2": (5, 480, 270, 1024), "P_C1": (0, 256, 256, 1024), "P_C4": (7, 480, 270, 256),
     "P_C5": (8, 480, 270, 256), "F_C2": (5, 1920, 1080, 256), "F_C3": (6, 1920, 1080, 256), "F_C4": (7, 1920, 1080, 64), "F_C5": (8, 3840, 2160, 36),
