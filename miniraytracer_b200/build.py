@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "miniraytracer_b200", "csrc")
 INC = os.path.join(ROOT, "include")
-LIB = os.path.join(ROOT, "miniraytracer_b200", "libmrt_b200.so")
+LIB = os.environ.get("MRT_LIB") or os.path.join(ROOT, "miniraytracer_b200", "libmrt_b200.so")   # MRT_LIB: A/B builds (tools only)
 EXE = os.path.join(ROOT, "miniraytracer_b200", "mrt_b200")
 
 HOST_SRCS = ["scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "scene_dump.cpp", "flatten.cpp", "host_api.cpp"]
