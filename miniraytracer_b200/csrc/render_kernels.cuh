@@ -9,8 +9,11 @@
 //     regroups the live paths between segments through a per-warp pool and bins; in modes W / P a lane keeps
 //     its path and is regenerated from the item stream at the next warp-converged point (ballot + popc
 //     prefix), so lanes do not idle while the longest path of a batch finishes;
+//   * mode B hands the frame out in chunks of decreasing size (guided self-scheduling: big chunks first, the last stretch in
+//     chunks of 1/4 and 1/16 of the size), so a launch does not end with warps waiting for a big chunk;
 //   * per-thread traversal stacks live in shared memory, interleaved by lane (word k of lane l at
-//     [k*32 + l]) so pushes/pops are bank-conflict free.
+//     [k*32 + l]) so pushes/pops are bank-conflict free;
+//   * BVH trees are traversed per lane or -- mode B, big trees -- warp-cooperatively (coop_tree.cuh).
 // Every accumulator element has exactly one writer: no float atomics, results are reproducible run to run.
 #pragma once
 #include "gpu_internal.h"
