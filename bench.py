@@ -67,15 +67,16 @@ class ClockSampler(threading.Thread):
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, n_gpus=1):
         super().__init__(daemon=True)
-        self.gpu = gpu_index
+        self.gpu = gpu_index        # the GPU whose median clock is reported as `sm_mhz`
+        self.n_gpus = n_gpus        # GPUs 0 .. n_gpus-1 are sampled (one process per GPU: rank 0 watches them all)
         self.samples = []
         self.proc = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in range(max(self.n_gpus, self.gpu + 1))), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.samples.append([c.strip() for c in line.split(",")])
@@ -86,10 +87,13 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per_gpu = [], [], set(), {}
         for s in self.samples:
             try:
-                sm.append(float(s[1])); mx.append(float(s[2]))
+                per_gpu.setdefault(int(s[0]), []).append(float(s[1]))
+                if int(s[0]) == self.gpu:
+                    sm.append(float(s[1]))
+                mx.append(float(s[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -98,7 +102,10 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if len(per_gpu) > 1:   # median SM clock of every GPU of the job
+            out["sm_mhz_per_gpu"] = [sorted(v)[len(v) // 2] for _, v in sorted(per_gpu.items())]
+        return out
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -248,12 +255,17 @@ class Workload:
             self._final2 = [self.final, torch.empty_like(self.final)]
             self._host2 = [self.host_out, torch.empty((self.H, self.W, 4), dtype=torch.float32, pin_memory=True)]
         k = self._frame & 1
+        trace = os.environ.get("MRT_BENCH_TRACE") == "1"   # host-side time of each sub-step (stderr), to see where the host blocks
+        t = [time.perf_counter()]
         r2 = api.Renderer(self.hs, self.local_rank)
+        t.append(time.perf_counter())
         r2.set_stream(self.stream.cuda_stream)
         r2.bind_accumulator(self.acc.data_ptr(), self.W, self.H)
         r2.render_async(self.W, self.H, self.spp, self.depth, sample_begin=self.s_begin, sample_end=self.s_end)
+        t.append(time.perf_counter())
         if self.world > 1:
             dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        t.append(time.perf_counter())
         done = torch.cuda.Event()
         if self.rank == 0:
             r2.finalize_device(self.acc.data_ptr(), self._final2[k].data_ptr(), self.W, self.H)
@@ -267,8 +279,13 @@ class Workload:
             done.record(self.stream)
         self._inflight.append((r2, done))
         self._frame += 1
+        t.append(time.perf_counter())
         while len(self._inflight) > 1:
             self._retire()
+        t.append(time.perf_counter())
+        if trace:
+            names = ["create+upload", "launch", "all_reduce call", "finalize+copy call", "retire previous"]
+            sys.stderr.write(f"[e2e rank {self.rank} frame {self._frame}] " + " ".join(f"{n}={1e3 * (b - a):.2f}ms" for n, a, b in zip(names, t, t[1:])) + "\n")
 
     def _retire(self):
         r, done = self._inflight.pop(0)
@@ -357,6 +374,10 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
         total_s = reduce_max(sum(a.elapsed_time(b) for a, b in ev)) / 1000.0
+        k_mine = sum(kernel_ms) / len(kernel_ms)
+        k_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(k_all, torch.tensor([k_mine], dtype=torch.float64, device=dev))
         rays_total = reduce_sum(float(sum(rays)))
         res = {
             "value": wl.paths_per_step * steps / total_s / 1e6, "ms_per_step": 1000.0 * total_s / steps,
@@ -364,6 +385,8 @@ def main():
             "kernel_ms": sum(kernel_ms) / len(kernel_ms), "rays_per_launch": sum(rays) / len(rays),
             "live_lane_frac": sum(rays) / max(1.0, 32.0 * sum(iters)), "wall_s": wall, "steps": steps, "warmup": warmup,
         }
+        if world > 1:
+            res["kernel_ms_per_rank"] = [round(float(t.item()), 3) for t in k_all]   # the step waits for the slowest GPU
         if coop[-1][0]:
             c = coop[-1]
             res["coop_trees"] = {"node_step_fill": c[1] / max(1.0, 32.0 * c[2]), "leaf_step_fill": c[3] / max(1.0, 32.0 * c[4])}
@@ -375,8 +398,9 @@ def main():
             for _ in range(e2e_steps):
                 wl.step_e2e()
             wl.drain_e2e()                       # every frame's D2H has landed in pinned host memory
-            barrier()
-            e2e_s = reduce_max(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+            e2e_s = reduce_max(time.perf_counter() - t0)   # max over ranks (the all-reduce inside every frame keeps them in step;
+            barrier()                                      #  a dist.barrier() costs tens of ms by itself and is not part of a frame)
             res["e2e"] = {"value": wl.paths_per_step * e2e_steps / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes(wl.hs.desc),
                           "d2h_bytes_per_step": wl.W * wl.H * 16, "steps": e2e_steps,
                           "image_mean": float(wl.host_out[..., :3].double().mean()) if rank == 0 else None}
@@ -399,10 +423,10 @@ def main():
 
     # ---------------------------------------------------------------- headline
     head = Workload(args.workload, rank, world, local_rank, args.spp, args.size)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, world)
     if rank == 0:
         sampler.start()
-    hres = measure(head, args.steps, args.warmup, max(1, min(args.steps, 3)))
+    hres = measure(head, args.steps, args.warmup, max(1, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     sm_count = head.r.info.sm_count
     peaks = measured_peaks()
@@ -433,6 +457,7 @@ def main():
             "grays_per_s": hres["grays_per_s"], "rays_per_path": hres["rays_per_path"], "live_lane_frac": hres["live_lane_frac"],
             "wall_s_timed_region": hres["wall_s"],
             "e2e": hres["e2e"],
+            "kernel_ms_per_rank": hres.get("kernel_ms_per_rank"),
             "gpu_launches": args.steps * 2,   # render kernel + finalize kernel per step (NCCL's kernels not counted)
             "roofline": roof,
             "clocks": clocks,

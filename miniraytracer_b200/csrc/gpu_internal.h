@@ -50,6 +50,10 @@ struct MrtScene {
     int *cancel_pinned = nullptr; // pinned staging word for the async write
     unsigned long long *poll_host = nullptr;   // pinned: [0] ticket [1] rays
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_up = nullptr;      // scene tables uploaded (recorded on poll_stream); the first render waits for it
+    bool upload_pending = false;
+    void *upload_pinned = nullptr;    // pinned staging of the upload (cached per process)
+    size_t upload_pinned_bytes = 0;
     // last render
     bool rendered = false;
     MrtRenderParams last;

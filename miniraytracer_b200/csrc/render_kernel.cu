@@ -214,7 +214,37 @@ static uint32_t *pool_acquire(int device, size_t words, size_t *got_words) {
 }
 static void pool_release(int device, uint32_t *ptr, size_t words) { devbuf_release(device, ptr, words * sizeof(uint32_t)); }
 
-struct SyncObjs { int device; cudaStream_t stream; cudaEvent_t ev0, ev1; };
+// pinned host staging for the scene upload (cudaHostAlloc costs milliseconds): same caching policy, at most 8 buffers / 256 MiB
+struct PinBuf { void *ptr; size_t bytes; };
+static std::vector<PinBuf> g_pin_free;
+static size_t g_pin_cached = 0;
+static void *pinbuf_acquire(size_t bytes, size_t *got_bytes) {
+    if (bytes < 4096) bytes = 4096;
+    {
+        std::lock_guard<std::mutex> lk(g_buf_mu);
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].bytes >= bytes && g_pin_free[i].bytes <= 2 * bytes) {
+                PinBuf b = g_pin_free[i];
+                g_pin_free.erase(g_pin_free.begin() + i);
+                g_pin_cached -= b.bytes;
+                *got_bytes = b.bytes;
+                return b.ptr;
+            }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got_bytes = bytes;
+    return p;
+}
+static void pinbuf_release(void *ptr, size_t bytes) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    if (g_pin_free.size() >= 8 || g_pin_cached + bytes > ((size_t) 256 << 20)) { cudaFreeHost(ptr); return; }
+    g_pin_free.push_back(PinBuf{ptr, bytes});
+    g_pin_cached += bytes;
+}
+
+struct SyncObjs { int device; cudaStream_t stream; cudaEvent_t ev0, ev1, ev_up; };
 static std::vector<SyncObjs> g_sync_free;
 static bool syncobjs_acquire(int device, SyncObjs *out) {
     {
@@ -222,14 +252,20 @@ static bool syncobjs_acquire(int device, SyncObjs *out) {
         for (size_t i = 0; i < g_sync_free.size(); i++)
             if (g_sync_free[i].device == device) { *out = g_sync_free[i]; g_sync_free.erase(g_sync_free.begin() + i); return true; }
     }
-    out->device = device; out->stream = nullptr; out->ev0 = out->ev1 = nullptr;
+    out->device = device; out->stream = nullptr; out->ev0 = out->ev1 = out->ev_up = nullptr;
     if (cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&out->ev0) != cudaSuccess ||
-        cudaEventCreate(&out->ev1) != cudaSuccess) return false;
+        cudaEventCreate(&out->ev1) != cudaSuccess || cudaEventCreateWithFlags(&out->ev_up, cudaEventDisableTiming) != cudaSuccess) return false;
     return true;
 }
 static void syncobjs_release(const SyncObjs &o) {
     std::lock_guard<std::mutex> lk(g_buf_mu);
-    if (g_sync_free.size() >= 32) { if (o.stream) cudaStreamDestroy(o.stream); if (o.ev0) cudaEventDestroy(o.ev0); if (o.ev1) cudaEventDestroy(o.ev1); return; }
+    if (g_sync_free.size() >= 32) {
+        if (o.stream) cudaStreamDestroy(o.stream);
+        if (o.ev0) cudaEventDestroy(o.ev0);
+        if (o.ev1) cudaEventDestroy(o.ev1);
+        if (o.ev_up) cudaEventDestroy(o.ev_up);
+        return;
+    }
     g_sync_free.push_back(o);
 }
 
@@ -281,7 +317,8 @@ extern "C" void mrt_gpu_destroy(MrtScene *s) {
     if (s->final_buf) devbuf_release(s->device, s->final_buf, s->final_bytes);
     if (s->argb_buf) devbuf_release(s->device, s->argb_buf, s->argb_bytes);
     if (s->poll_host && !pinned_slot_release(s->poll_host)) cudaFreeHost(s->poll_host);   // control words live in the scene allocation
-    if (s->poll_stream || s->ev0 || s->ev1) syncobjs_release(SyncObjs{s->device, s->poll_stream, s->ev0, s->ev1});
+    if (s->upload_pinned) pinbuf_release(s->upload_pinned, s->upload_pinned_bytes);   // (the poll stream, which carried the copy, was synchronised above)
+    if (s->poll_stream || s->ev0 || s->ev1) syncobjs_release(SyncObjs{s->device, s->poll_stream, s->ev0, s->ev1, s->ev_up});
     delete s;
 }
 
@@ -418,12 +455,26 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     pk.add(d->lights, (size_t) d->n_lights, &v.lights);
     const size_t ctrl_off = pk.reserve(256);   // ticket | counters[4] | max_bits | cancel, zero-initialised
     {
-        std::vector<unsigned char> staging(pk.total, 0);
-        for (const Packer::Item &it : pk.items) memcpy(staging.data() + it.offset, it.host, it.bytes);
+        SyncObjs so;
+        const bool ok = syncobjs_acquire(s->device, &so);
+        s->poll_stream = so.stream; s->ev0 = so.ev0; s->ev1 = so.ev1; s->ev_up = so.ev_up;
+        if (!ok) { cudaGetLastError(); set_error("cudaStreamCreate / cudaEventCreate failed"); return fail(MRT_E_CUDA); }
+    }
+    {
+        // The tables go through a pinned staging buffer and ONE asynchronous copy on the scene's own non-blocking stream; the first
+        // render waits for it with an event.  (A plain cudaMemcpy runs on the legacy default stream and so waits for whatever
+        // another scene is rendering on it: measured, it serialised the upload of frame k+1 behind the render of frame k.)
+        unsigned char *staging = (unsigned char *) pinbuf_acquire(pk.total, &s->upload_pinned_bytes);
+        if (!staging) { set_error("cudaHostAlloc upload staging failed"); return fail(MRT_E_CUDA); }
+        s->upload_pinned = staging;
+        memset(staging, 0, pk.total);
+        for (const Packer::Item &it : pk.items) memcpy(staging + it.offset, it.host, it.bytes);
         unsigned char *base = (unsigned char *) devbuf_acquire(s->device, pk.total, &s->scene_bytes);
         if (!base) { set_error(std::string("cudaMalloc scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
         s->scene_base = base;
-        if (cudaMemcpy(base, staging.data(), pk.total, cudaMemcpyHostToDevice) != cudaSuccess) { set_error(std::string("cudaMemcpy scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
+        if (cudaMemcpyAsync(base, staging, pk.total, cudaMemcpyHostToDevice, s->poll_stream) != cudaSuccess ||
+            cudaEventRecord(s->ev_up, s->poll_stream) != cudaSuccess) { set_error(std::string("cudaMemcpyAsync scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
+        s->upload_pending = true;
         for (const Packer::Item &it : pk.items) *it.dev = base + it.offset;
         s->counters = (unsigned long long *) (base + ctrl_off);          // 8 x 8 bytes
         s->ticket = (unsigned int *) (base + ctrl_off + 64);
@@ -454,14 +505,17 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
         s->poll_host = (unsigned long long *) slot;
         s->cancel_pinned = (int *) ((unsigned char *) slot + 32);
     }
-    {
-        SyncObjs so;
-        const bool ok = syncobjs_acquire(s->device, &so);
-        s->poll_stream = so.stream; s->ev0 = so.ev0; s->ev1 = so.ev1;
-        if (!ok) { cu(cudaGetLastError(), "cudaStreamCreate / cudaEventCreate"); set_error("cudaStreamCreate / cudaEventCreate failed"); return fail(MRT_E_CUDA); }
-    }
+
     *out = s;
     return MRT_OK;
+}
+
+// The scene tables and the control block travel on the poll stream (mrt_gpu_scene_upload); whatever touches them on the render
+// stream first is ordered after that copy by an event.
+static cudaError_t order_after_upload(MrtScene *s) {
+    if (!s->upload_pending) return cudaSuccess;
+    s->upload_pending = false;
+    return cudaStreamWaitEvent(s->stream, s->ev_up, 0);
 }
 
 extern "C" int mrt_gpu_set_tuning(MrtScene *s, const MrtTuning *t) {
@@ -718,6 +772,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         }
         a.stage = reinterpret_cast<float4 *>(s->stage_dev);
     }
+    CUDA_TRY(order_after_upload(s));
     CUDA_TRY(cudaMemsetAsync(s->cancel_dev, 0, sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned int), s->stream));
     s->final_is_running_mean = false;
@@ -887,6 +942,7 @@ extern "C" int mrt_gpu_tonemap_device(MrtScene *s, const void *img_dev, void *ar
     if (!s || !img_dev || !argb_dev) { set_error("mrt_gpu_tonemap_device: null argument"); return MRT_E_INVALID; }
     CUDA_TRY(cudaSetDevice(s->device));
     const uint32_t n = width * height;
+    CUDA_TRY(order_after_upload(s));
     CUDA_TRY(cudaMemsetAsync(s->max_bits, 0, sizeof(unsigned int), s->stream));
     max_luminance_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>((const float4 *) img_dev, n, s->max_bits);
     tonemap_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>((const float4 *) img_dev, (uint32_t *) argb_dev, n, s->max_bits);
