@@ -361,7 +361,7 @@ def main():
         barrier()
         stream = wl.stream
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        kernel_ms, rays, iters, coop = [], [], [], []
+        kernel_ms, rays, iters, coop, busy, ssum = [], [], [], [], [], []
         t0 = time.perf_counter()
         for i in range(steps):
             ev[i][0].record(stream)
@@ -370,6 +370,9 @@ def main():
             st = wl.r.stats()                    # waits for the render kernel of this step
             kernel_ms.append(st["kernel_ms"]); rays.append(st["rays"]); iters.append(st["warp_iterations"])
             coop.append((st["coop_trees"], st["coop_node_items"], st["coop_node_steps"], st["coop_leaf_items"], st["coop_leaf_steps"]))
+            if st["warps"]:   # mode B: share of the launch the average warp was at work, share of that spent summing staged samples
+                busy.append(st["warp_time_sum_ns"] / max(1, st["warps"] * st["warp_span_ns"]))
+                ssum.append(st["stage_sum_ns"] / max(1, st["warp_time_sum_ns"]))
             flush.zero_()                        # L2 flush between timed steps (outside the event pairs)
         barrier()
         wall = time.perf_counter() - t0
@@ -385,6 +388,8 @@ def main():
             "kernel_ms": sum(kernel_ms) / len(kernel_ms), "rays_per_launch": sum(rays) / len(rays),
             "live_lane_frac": sum(rays) / max(1.0, 32.0 * sum(iters)), "wall_s": wall, "steps": steps, "warmup": warmup,
         }
+        if busy:
+            res["warp_busy_frac"], res["stage_sum_frac"] = sum(busy) / len(busy), sum(ssum) / len(ssum)
         if world > 1:
             res["kernel_ms_per_rank"] = [round(float(t.item()), 3) for t in k_all]   # the step waits for the slowest GPU
         if coop[-1][0]:
@@ -458,6 +463,9 @@ def main():
             "wall_s_timed_region": hres["wall_s"],
             "e2e": hres["e2e"],
             "kernel_ms_per_rank": hres.get("kernel_ms_per_rank"),
+            # mode B, rank 0: share of the launch the average warp was at work (the rest: warps out of tickets waiting for the last
+            # one) and share of that warp time spent adding up the staged samples at chunk ends (mrt_gpu_stats)
+            "warp_busy_frac": hres.get("warp_busy_frac"), "stage_sum_frac": hres.get("stage_sum_frac"),
             "gpu_launches": args.steps * 2,   # render kernel + finalize kernel per step (NCCL's kernels not counted)
             "roofline": roof,
             "clocks": clocks,
@@ -488,6 +496,8 @@ def main():
                          "config": config_dict(name, wl.scene, wl.W, wl.H, wl.N, wl.depth), "reduced": wl.reduced or None}
                 if "coop_trees" in res:
                     entry["coop_trees"] = res["coop_trees"]
+                if "warp_busy_frac" in res:
+                    entry["warp_busy_frac"], entry["stage_sum_frac"] = res["warp_busy_frac"], res["stage_sum_frac"]
                 per[name] = entry
             wl.close()
         if rank == 0:

@@ -149,6 +149,11 @@ typedef struct MrtRenderStats {
     /* cooperative traversal: steps executed (summed over warps) and work items popped in them: items / (32 * steps) =
        lane fill of the node (box tests) and leaf (primitive tests) phases */
     uint64_t coop_node_steps, coop_node_items, coop_leaf_steps, coop_leaf_items;
+    /* mode B: %globaltimer at entry and exit of every warp.  warp_time_sum_ns / (warps * warp_span_ns) = share of the launch the
+       average warp was at work (the rest: warps that ran out of tickets wait for the slowest one) */
+    uint64_t warp_time_sum_ns, warp_span_ns, first_exit_ns;   /* first_exit_ns: first warp exit, relative to the first warp entry */
+    uint32_t warps, reserved;
+    uint64_t stage_sum_ns;   /* mode B: warp time spent adding up the staged samples at the ends of the chunks (part of warp_time_sum_ns) */
 } MrtRenderStats;
 /* Statistics of the last finished render (blocks like mrt_gpu_wait). */
 int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out);

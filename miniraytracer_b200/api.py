@@ -78,7 +78,8 @@ class DeviceInfo(C.Structure):
 class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("nonfinite", C.c_uint64), ("warp_iterations", C.c_uint64), ("kernel_ms", C.c_float),
                 ("grid", C.c_uint32), ("block", C.c_uint32), ("smem_bytes", C.c_uint32), ("mode", C.c_uint32), ("coop_trees", C.c_uint32),
-                ("coop_node_steps", C.c_uint64), ("coop_node_items", C.c_uint64), ("coop_leaf_steps", C.c_uint64), ("coop_leaf_items", C.c_uint64)]
+                ("coop_node_steps", C.c_uint64), ("coop_node_items", C.c_uint64), ("coop_leaf_steps", C.c_uint64), ("coop_leaf_items", C.c_uint64),
+                ("warp_time_sum_ns", C.c_uint64), ("warp_span_ns", C.c_uint64), ("first_exit_ns", C.c_uint64), ("warps", C.c_uint32), ("reserved", C.c_uint32), ("stage_sum_ns", C.c_uint64)]
 
 
 MRT_RENDER_ACCUMULATE = 1

@@ -453,7 +453,7 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
     pk.add(d->perlin_perm, d->perlin_perm ? 768 : 0, &v.perlin_perm);
     pk.add(d->image, (size_t) d->n_image_bytes, &v.image);
     pk.add(d->lights, (size_t) d->n_lights, &v.lights);
-    const size_t ctrl_off = pk.reserve(256);   // ticket | counters[4] | max_bits | cancel, zero-initialised
+    const size_t ctrl_off = pk.reserve(256);   // counters[12] | ticket | max_bits | cancel, zero-initialised
     {
         SyncObjs so;
         const bool ok = syncobjs_acquire(s->device, &so);
@@ -476,9 +476,9 @@ extern "C" int mrt_gpu_scene_upload(const MrtSceneDesc *d, MrtScene **out) {
             cudaEventRecord(s->ev_up, s->poll_stream) != cudaSuccess) { set_error(std::string("cudaMemcpyAsync scene: ") + cudaGetErrorString(cudaGetLastError())); return fail(MRT_E_CUDA); }
         s->upload_pending = true;
         for (const Packer::Item &it : pk.items) *it.dev = base + it.offset;
-        s->counters = (unsigned long long *) (base + ctrl_off);          // 8 x 8 bytes
-        s->ticket = (unsigned int *) (base + ctrl_off + 64);
-        s->max_bits = (unsigned int *) (base + ctrl_off + 128);
+        s->counters = (unsigned long long *) (base + ctrl_off);          // 12 x 8 bytes
+        s->ticket = (unsigned int *) (base + ctrl_off + 128);
+        s->max_bits = (unsigned int *) (base + ctrl_off + 160);
         s->cancel_dev = (int *) (base + ctrl_off + 192);
     }
     v.root = d->root;
@@ -651,7 +651,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     // default: only where it pays -- big trees (triangle meshes); the small sphere / box trees of scenes 0, 1, 7 are faster per lane
     // (profiles/r2_notes.md)
     const bool coop = coop_ok && (tn.coop_trees == 2u || (tn.coop_trees == 0u && s->n_node2 >= 1024u));
-    const void *kernel = variant->get(coop ? 3 : (binned ? 2 : (mode_w ? 1 : 0)), minb);
+    const int seq = (binned && ns <= kStageBlock) ? 2 : 0;   // few samples per pixel: the instantiation that sums a pixel's samples sequentially
+    const void *kernel = variant->get(coop ? 3 + seq : (binned ? 2 + seq : (mode_w ? 1 : 0)), minb);
     const uint32_t stack_words = coop ? s->stack_words_coop : s->stack_words;
     uint32_t n_bins = 1;
     a.pool = nullptr;
@@ -778,7 +779,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     s->final_is_running_mean = false;
     const bool cont = (p->flags & MRT_RENDER_CONTINUE) && s->rendered;
     if (!cont) {
-        CUDA_TRY(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, 12 * sizeof(unsigned long long), s->stream));
         CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
         s->stat_samples = 0;
     }
@@ -839,7 +840,7 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     if (!s->rendered) { set_error("mrt_gpu_stats: nothing rendered yet"); return MRT_E_STATE; }
     int rc = mrt_gpu_wait(s);
     if (rc) return rc;
-    unsigned long long c[8];
+    unsigned long long c[12];
     CUDA_TRY(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->rays = c[0];
@@ -853,6 +854,14 @@ extern "C" int mrt_gpu_stats(MrtScene *s, MrtRenderStats *out) {
     out->mode = s->last_mode;
     out->coop_trees = s->last_coop ? 1u : 0u;
     out->coop_node_steps = c[4]; out->coop_node_items = c[5]; out->coop_leaf_steps = c[6]; out->coop_leaf_items = c[7];
+    if (c[8]) {   // mode B: ~first entry | last exit | sum of (exit - entry) | ~first exit
+        const unsigned long long t_first = ~c[8];
+        out->warp_span_ns = c[9] - t_first;
+        out->warp_time_sum_ns = c[10];
+        out->first_exit_ns = ~c[11] - t_first;
+        out->warps = s->last_grid * (s->last_block / 32u);
+        out->stage_sum_ns = c[3];
+    }
     return MRT_OK;
 }
 

@@ -55,6 +55,7 @@ struct RenderArgs {
 };
 
 constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr uint32_t kStageBlock = 128;   // mode B: launches with up to this many samples per pixel add them up sequentially (SEQ, see render_pixel_binned)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -331,7 +332,17 @@ __device__ __forceinline__ uint32_t ray_class(const RenderArgs &a, const Path &p
     return c;
 }
 
-template <uint32_t FEAT, int MINB, bool COOP>
+__device__ __forceinline__ unsigned long long warp_clock_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#else
+    return 1ull;   // CPU build of the kernels (tests/host_emul)
+#endif
+}
+
+template <uint32_t FEAT, int MINB, bool COOP, bool SEQ>
 __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const RenderArgs a) {
     extern __shared__ uint32_t smem_stack[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -354,6 +365,12 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t ns = a.s_end - a.s_begin;
     unsigned long long rays = 0, nonfinite = 0, iters = 0;
+    if (lane == 0) {   // when the warps were at work (MrtRenderStats.warp_time_sum_ns ...): nothing kept in a register across the launch
+        const unsigned long long t_entry = warp_clock_ns();
+        atomicMax(&a.counters[8], ~t_entry);
+        atomicAdd(&a.counters[10], 0ull - t_entry);
+    }
+
 
     for (;;) {
         uint32_t task = 0;
@@ -465,32 +482,61 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         }
         __syncwarp();
         __threadfence_block();   // this warp's staged samples (written by other lanes) are visible to every lane
+        // Sum of a pixel's staged samples, in an order that depends on nothing but the samples per pixel of the launch.  Two forms,
+        // two instantiations (SEQ), so that neither changes the register allocation of the other's segment loop:
+        const unsigned long long t_sum0 = warp_clock_ns();
+        if constexpr (SEQ) {
+            // ns <= kStageBlock (the slice of a multi-GPU render, low-spp frames): lane = pixel, its samples added up one after the
+            // other -- the reference's own order (main.cpp:154-166) -- with eight loads in flight per lane, 32 pixels per pass.  A
+            // chunk costs 16 rounds of memory latency; lane-strided and one pixel at a time it cost 128 rounds, and the warp time spent
+            // here went 3.7 % -> 1.4 % on a 128-sample slice of C2 (MrtRenderStats.stage_sum_ns; profiles/r2_notes.md).
 #pragma unroll 1
-        for (uint32_t k = 0; k < kp; k++) {
-            // samples k*ns .. k*ns+ns-1 of pixel k: lane l adds items l, l+32, ... in order, then a fixed shuffle tree
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 *src = stage + k * ns;
-            uint32_t i = lane;
+            for (uint32_t k0 = 0; k0 < kp; k0 += 32u) {
+                if (k0 + lane < kp) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 *src = stage + (k0 + lane) * ns;
 #pragma unroll 1
-            for (; i + 7u * 32u < ns; i += 8u * 32u) {   // eight loads in flight, added in item order
-                float4 q[8];
+                    for (uint32_t i = 0; i < ns; i += 8u) {
+                        float4 q[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) q[j] = __ldcs(src + i + 32u * j);
+                        for (int j = 0; j < 8; j++) q[j] = (i + j < ns) ? __ldcs(src + i + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 8; j++) { v.x += q[j].x; v.y += q[j].y; v.z += q[j].z; v.w += q[j].w; }
+                        for (int j = 0; j < 8; j++) { v.x += q[j].x; v.y += q[j].y; v.z += q[j].z; v.w += q[j].w; }   // + 0.0f past the end: exact (v is never -0)
+                    }
+                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + k0 + lane) : pix0 + k0 + lane;
+                    if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    a.acc[pix] = v;
+                }
             }
+        } else {
+            // more samples per pixel: lane l adds items l, l+32, ... in order (eight loads in flight), then a fixed shuffle tree
 #pragma unroll 1
-            for (; i < ns; i += 32u) {
-                const float4 q = __ldcs(src + i);
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-            }
-            v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-            if (lane == 0) {
-                const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
-                if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                a.acc[pix] = v;
+            for (uint32_t k = 0; k < kp; k++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *src = stage + k * ns;
+                uint32_t i = lane;
+#pragma unroll 1
+                for (; i + 7u * 32u < ns; i += 8u * 32u) {
+                    float4 q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) q[j] = __ldcs(src + i + 32u * j);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { v.x += q[j].x; v.y += q[j].y; v.z += q[j].z; v.w += q[j].w; }
+                }
+#pragma unroll 1
+                for (; i < ns; i += 32u) {
+                    const float4 q = __ldcs(src + i);
+                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                }
+                v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                if (lane == 0) {
+                    const uint32_t pix = a.order ? __ldg(a.order + pix0 + k) : pix0 + k;
+                    if (a.accumulate) { float4 o = a.acc[pix]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    a.acc[pix] = v;
+                }
             }
         }
+        if (lane == 0) atomicAdd(&a.counters[3], warp_clock_ns() - t_sum0);   // MrtRenderStats.stage_sum_ns
         __syncwarp();
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -505,18 +551,22 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
             atomicAdd(&a.counters[4], cs_node_steps); atomicAdd(&a.counters[5], cs_node_items);
             atomicAdd(&a.counters[6], cs_leaf_steps); atomicAdd(&a.counters[7], cs_leaf_items);
         }
+        const unsigned long long t_exit = warp_clock_ns();   // counters[10] = sum of (exit - entry), modulo 2^64
+        atomicMax(&a.counters[9], t_exit); atomicAdd(&a.counters[10], t_exit); atomicMax(&a.counters[11], ~t_exit);
     }
 }
 
 // kernel entry for a feature mask (defined once per render_variant_*.cu); kind: 0 = pixel per lane,
 // 1 = pixel per warp, 2 = pixel per warp with binned path pool, 3 = binned + warp-cooperative tree traversal (only
-// instantiated for masks with MRT_FEAT_TREES)
+// instantiated for masks with MRT_FEAT_TREES); 4, 5 = 2, 3 for launches with at most kStageBlock samples per pixel (SEQ)
 template <uint32_t FEAT, int MINB>
 inline const void *variant_kernel_minb(int kind) {
     if constexpr ((FEAT & MRT_FEAT_TREES) != 0) {
-        if (kind == 3) return (const void *) render_pixel_binned<FEAT, MINB, true>;
+        if (kind == 3) return (const void *) render_pixel_binned<FEAT, MINB, true, false>;
+        if (kind == 5) return (const void *) render_pixel_binned<FEAT, MINB, true, true>;
     }
-    if (kind >= 2) return (const void *) render_pixel_binned<FEAT, MINB, false>;
+    if (kind == 4) return (const void *) render_pixel_binned<FEAT, MINB, false, true>;
+    if (kind >= 2) return (const void *) render_pixel_binned<FEAT, MINB, false, false>;
     return kind ? (const void *) render_pixel_per_warp<FEAT, MINB> : (const void *) render_pixel_per_lane<FEAT, MINB>;
 }
 template <uint32_t FEAT>

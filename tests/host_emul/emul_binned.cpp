@@ -30,11 +30,13 @@ struct FileHeader {
 static RenderArgs g_args;
 static char g_mode = 'B';
 static bool g_coop = false;
+static bool g_seq = false;   // launches with <= kStageBlock samples per pixel use the SEQ instantiation (render_kernel.cu)
 static void entry(void *) {
     if (g_mode == 'W') render_pixel_per_warp<MRT_FEAT_ALL, 6>(g_args);
     else if (g_mode == 'P') render_pixel_per_lane<MRT_FEAT_ALL, 6>(g_args);
-    else if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true>(g_args);
-    else render_pixel_binned<MRT_FEAT_ALL, 6, false>(g_args);
+    else if (g_seq) { if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true, true>(g_args); else render_pixel_binned<MRT_FEAT_ALL, 6, false, true>(g_args); }
+    else if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true, false>(g_args);
+    else render_pixel_binned<MRT_FEAT_ALL, 6, false, false>(g_args);
 }
 
 int main(int argc, char **argv) {
@@ -73,6 +75,7 @@ int main(int argc, char **argv) {
     const uint32_t ns = s1 - s0, n_pixels = CW * CH;
     a.crop_x0 = x0; a.crop_y0 = y0; a.crop_w = CW; a.n_pixels = n_pixels;
     a.width = W; a.height = H; a.sqrt_n = sq; a.s_begin = s0; a.s_end = s1; a.max_bounces = depth; a.seed = seed;
+    g_seq = (s1 - s0) <= kStageBlock;
     a.accumulate = 0;
     a.stack_words = d.stack_words ? d.stack_words : 64;
     if (g_coop) {
@@ -110,7 +113,7 @@ int main(int argc, char **argv) {
     std::vector<float4> acc(n_pixels, make_float4(0, 0, 0, 0));
     a.acc = acc.data();
     unsigned int ticket = 0;
-    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long counters[12] = {0};
     int cancel = 0;
     a.ticket = &ticket; a.counters = counters; a.cancel = &cancel; a.order = nullptr;
     const uint32_t warps = kWarpsPerBlock;

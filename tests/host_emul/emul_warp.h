@@ -141,6 +141,7 @@ inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }

@@ -255,6 +255,34 @@ def test_progressive_passes_single_gpu():
     assert res["n_bad"] == 0, res
 
 
+def test_few_samples_are_added_in_sample_order_and_warp_times_are_reported():
+    """Launches with at most 128 samples per pixel run the SEQ instantiation of mode B: a pixel's samples are added one after
+    the other in sample order (the reference's loop, main.cpp:154-166), so the accumulator equals the float32 running sum of
+    one-sample launches; more samples per pixel use lane-strided partial sums (same samples, sum within rounding).  Also the
+    mode-B timing counters of MrtRenderStats."""
+    w, h, spp = 40, 22, 121
+    acc, st = _gpu_render(5, w, h, spp)
+    assert st["mode"] == api.MODE_BINNED
+    run = np.zeros_like(acc)
+    hs = api.HostScene(5, w, h)
+    r = api.Renderer(hs, 0)
+    try:
+        for s in range(spp):
+            r.render_async(w, h, spp, 32, api.DEFAULT_SEED, sample_begin=s, sample_end=s + 1)
+            run = (run + r.readback()).astype(np.float32)
+        np.testing.assert_array_equal(acc, run)
+        r.render_async(w, h, 169, 32, api.DEFAULT_SEED)     # > 128 samples per pixel
+        big, st2 = r.readback(), r.stats()
+    finally:
+        r.close()
+        hs.close()
+    np.testing.assert_array_equal(big[..., 3], np.float32(169))
+    assert st2["warps"] == st2["grid"] * st2["block"] // 32 and st2["warp_span_ns"] > 0
+    assert 0 < st2["warp_time_sum_ns"] <= st2["warps"] * st2["warp_span_ns"]
+    assert 0 < st2["stage_sum_ns"] < st2["warp_time_sum_ns"] and st2["first_exit_ns"] <= st2["warp_span_ns"]
+    assert abs(st2["warp_span_ns"] * 1e-6 - st2["kernel_ms"]) < 0.5 * st2["kernel_ms"] + 0.05
+
+
 def test_binned_result_does_not_depend_on_the_schedule():
     """Mode B sums the finished samples of a pixel in item order from its staging array, so the accumulator is
     bit-identical whatever the bins, the chunk size or the launch bounds (i.e. whichever lane ran which path)."""

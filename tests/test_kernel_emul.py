@@ -24,12 +24,26 @@ def _same(acc, ref, rays, ref_rays):
 
 @needs_ref
 @pytest.mark.parametrize("scene,w,h,spp,bins", [(5, 24, 13, 36, 1), (5, 24, 13, 36, 2), (5, 24, 13, 36, 3), (6, 20, 11, 36, 2),
-                                                 (7, 20, 11, 16, 2), (8, 16, 9, 16, 2), (0, 16, 16, 9, 2), (5, 7, 3, 1, 2)])
+                                                 (7, 20, 11, 16, 2), (8, 16, 9, 16, 2), (0, 16, 16, 9, 2), (5, 7, 3, 1, 2),
+                                                 (5, 6, 4, 169, 2), (5, 3, 2, 1089, 2)])   # > 128 samples per pixel: the lane-strided sums
 def test_mode_b_kernel_matches_oracle(emul_kernel_bin, scene, w, h, spp, bins):
     ref, rmeta = oracle_util.ref_render(scene, w, h, spp)
     acc, meta = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, bins=bins)
     assert meta["info"]["tasks"] > 4 or w * h < 32          # several tickets per warp
     _same(acc, ref, meta["rays"], rmeta["rays"])
+
+
+@pytest.mark.parametrize("scene,w,h,spp", [(5, 9, 5, 36), (8, 6, 4, 16)])
+def test_mode_b_sums_few_samples_in_the_reference_order(emul_kernel_bin, scene, w, h, spp):
+    """Up to 128 samples per pixel mode B (the SEQ instantiation) adds a pixel's samples one after the other in sample order,
+    the order of the reference's own loop (main.cpp:154-166): the accumulator EQUALS the float32 running sum of the samples
+    rendered one by one."""
+    acc, _ = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, bins=2)
+    run = np.zeros_like(acc)
+    for s in range(spp):
+        one, _ = oracle_util.emul_binned(emul_kernel_bin, scene, w, h, spp, bins=2, s0=s, s1=s + 1)
+        run = (run + one).astype(np.float32)
+    np.testing.assert_array_equal(acc, run)
 
 
 @needs_ref

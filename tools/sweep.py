@@ -21,7 +21,7 @@ CASES = {
 
 def measure(case, tuning, reps=2, depth=32):
     reps = int(os.environ.get("MRT_SWEEP_REPS", reps))
-    scene, w, h, spp = CASES[case]
+    scene, w, h, spp = CASES[case] if case in CASES else tuple(int(v) for v in case.split(":"))   # ad hoc: scene:W:H:spp
     hs = api.HostScene(scene, w, h)
     r = api.Renderer(hs, 0, tuning)
     best = None
@@ -37,6 +37,10 @@ def measure(case, tuning, reps=2, depth=32):
            "coop_node_fill": best["coop_node_items"] / max(1, 32 * best["coop_node_steps"]),
            "coop_leaf_fill": best["coop_leaf_items"] / max(1, 32 * best["coop_leaf_steps"]),
            "coop_node_items_per_ray": best["coop_node_items"] / max(1, best["rays"])}
+    if best.get("warps"):
+        res["warp_busy_frac"] = best["warp_time_sum_ns"] / max(1, best["warps"] * best["warp_span_ns"])
+        res["warp_span_ms"] = best["warp_span_ns"] / 1e6
+        res["first_exit_ms"] = best["first_exit_ns"] / 1e6
     res["tuning"] = {k: v for k, v in tuning.items() if v}
     return res
 
