@@ -485,7 +485,7 @@ def main():
             heavy = wl.paths_per_step > 3e9
             # heavy configs: one timed step; the warm-up renders a 64-sample slice (kernel and caches warm, clocks up)
             warm_slice = (wl.s_begin, min(wl.s_end, wl.s_begin + 64)) if heavy else None
-            res = measure(wl, 1 if heavy else 3, 1 if heavy else 2, 1, warm_slice)
+            res = measure(wl, 1 if heavy else 3, 1 if heavy else 2, 1 if heavy else 3, warm_slice)
             if rank == 0:
                 entry = {"value": res["value"], "unit": "Mpaths/s", "grays_per_s": res["grays_per_s"], "kernel_ms": res["kernel_ms"],
                          "ms_per_step": res["ms_per_step"], "rays_per_path": res["rays_per_path"], "lanes": res["live_lane_frac"],

@@ -270,37 +270,41 @@ static void syncobjs_release(const SyncObjs &o) {
 }
 
 extern "C" int mrt_gpu_init(int device, MrtDeviceInfo *info) {
-    int n = 0;
-    CUDA_TRY(cudaGetDeviceCount(&n));
-    if (device < 0 || device >= n) { set_error("mrt_gpu_init: no such CUDA device"); return MRT_E_INVALID; }
+    // Everything asked of the driver here is cached per device: cudaGetDeviceProperties costs ~100 ms and the clock-rate attribute
+    // 5 - 100 ms PER CALL (measured: it is answered by the GPU, not from a table), and a renderer is created per frame.
+    static std::mutex mu;
+    static MrtDeviceInfo cached[64];
+    static bool have[64];
+    static int n_devices = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (n_devices < 0) {
+        int n = 0;
+        CUDA_TRY(cudaGetDeviceCount(&n));
+        n_devices = n;
+    }
+    if (device < 0 || device >= n_devices || device >= 64) { set_error("mrt_gpu_init: no such CUDA device"); return MRT_E_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
-    int cc_major = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
-    if (cc_major != 10) {
+    if (!have[device]) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        MrtDeviceInfo &d = cached[device];
+        memset(&d, 0, sizeof(d));
+        d.device = device;
+        d.sm_count = prop.multiProcessorCount;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        d.clock_khz = khz;
+        d.cc_major = prop.major;
+        d.cc_minor = prop.minor;
+        d.total_mem = prop.totalGlobalMem;
+        strncpy(d.name, prop.name, sizeof(d.name) - 1);
+        have[device] = true;
+    }
+    if (cached[device].cc_major != 10) {
         set_error("mrt_gpu_init: kernels are built for sm_100a only");
         return MRT_E_CUDA;
     }
-    if (info) {   // cudaGetDeviceProperties is slow (~100 ms): only on request, cached per device
-        static cudaDeviceProp cached[64];
-        static bool have[64];
-        if (device < 64 && !have[device]) {
-            CUDA_TRY(cudaGetDeviceProperties(&cached[device], device));
-            have[device] = true;
-        }
-        cudaDeviceProp prop;
-        if (device < 64) prop = cached[device];
-        else CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        memset(info, 0, sizeof(*info));
-        info->device = device;
-        info->sm_count = prop.multiProcessorCount;
-        int khz = 0;
-        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
-        info->clock_khz = khz;
-        info->cc_major = prop.major;
-        info->cc_minor = prop.minor;
-        info->total_mem = prop.totalGlobalMem;
-        strncpy(info->name, prop.name, sizeof(info->name) - 1);
-    }
+    if (info) *info = cached[device];
     return MRT_OK;
 }
 
