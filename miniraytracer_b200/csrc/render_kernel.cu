@@ -703,9 +703,14 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         const uint64_t total = (uint64_t) n_pixels * ns;
         // >= 10 big tasks per resident warp for list scenes (chunks cost about the same; the end of the launch is balanced by the
         // small last chunks, below), >= 32 for scenes with trees, whose chunks differ several-fold in cost (mesh vs background
-        // pixels: measured 176 -> 249 ms on a 960x540x256 frame of scene 7 with 10)
-        uint64_t target = total / ((uint64_t) resident_warps * (s->has_trees ? 32u : 10u));
-        if (target > 4096u) target = 4096u;
+        // pixels: measured 176 -> 249 ms on a 960x540x256 frame of scene 7 with 10), >= 64 for the per-lane tree scenes (15-fold:
+        // 178 -> 156 ms on that frame, warps at work 78 % -> 95 % of the launch, although fewer lanes hold a path: 93 % -> 88 %)
+        uint64_t target = total / ((uint64_t) resident_warps * (s->has_trees ? (coop ? 32u : 64u) : 10u));
+        // big chunks: 4096 paths; 2048 for the per-lane tree scenes, whose chunks differ 15-fold in cost (pixels on the glass / fog of
+        // scene 7): a heavy 4096-path chunk handed out late outlasts the whole guided tail (warps at work 94 % -> 99.9 % of a
+        // 512-sample 1080p slice, 1111 -> 1065 ms; the triangle meshes lose 0.7 % with 2048; profiles/r2_notes.md)
+        const uint64_t cap = tn.chunk_paths ? tn.chunk_paths : ((s->has_trees && !coop) ? 2048u : 4096u);
+        if (target > cap) target = cap;
         if (target < 256u) target = 256u;
         K = (uint32_t) (target / ns);
         if (tn.chunk_pixels) K = tn.chunk_pixels;
@@ -745,7 +750,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         // small chunk, not a big one (with 18 big chunks per warp, the 1/8 slice of an 8-GPU run, the idle end was 3-5 %
         // of the launch; profiles/r2_notes.md).  MrtTuning.chunk_pixels = uniform chunks of that size.
         uint32_t k1 = K / 4u ? K / 4u : 1u, k2 = K / 16u ? K / 16u : 1u;
-        uint64_t tail = tn.chunk_pixels ? 0u : (uint64_t) 2u * resident_warps * K;     // pixels handed out in small chunks
+        uint64_t tail = tn.chunk_pixels ? 0u : (uint64_t) (tn.tail_tasks ? tn.tail_tasks : 2u) * resident_warps * K;     // pixels handed out in small chunks
         if (tail > n_pixels / 4u) tail = n_pixels / 4u;
         if (k1 == K) tail = 0;
         const uint32_t p1 = n_pixels - (uint32_t) tail;                                 // run 0: [0, p1) in chunks of K
