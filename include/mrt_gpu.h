@@ -117,7 +117,8 @@ typedef struct MrtTuning {
     uint32_t coop_leaf_batch; /* cooperative traversal: leaves queued before a leaf step runs, 1..32 (0 = default) */
     uint32_t chunk_paths;  /* mode B: paths per big warp task (0 = by scene type); the guided tail of small tasks stays */
     uint32_t tail_tasks;   /* mode B: big tasks per resident warp handed out in small pieces at the end (0 = by scene type) */
-    uint32_t reserved[6];
+    uint32_t blocks_per_sm; /* resident blocks per SM actually launched (0 = all that fit) */
+    uint32_t reserved[5];
 } MrtTuning;
 #define MRT_MODE_AUTO 0u
 #define MRT_MODE_PER_LANE 1u /* a lane owns a pixel and adds its samples in the reference's order (main.cpp:154-166) */

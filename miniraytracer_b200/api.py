@@ -56,7 +56,7 @@ class Tuning(C.Structure):
     """MrtTuning: scheduling knobs (all zero = the measured defaults)."""
     _fields_ = [("mode", C.c_uint32), ("bins", C.c_uint32), ("min_blocks", C.c_uint32), ("chunk_pixels", C.c_uint32),
                 ("variant_all", C.c_uint32), ("z_order", C.c_uint32), ("coop_trees", C.c_uint32), ("coop_leaf_batch", C.c_uint32),
-                ("chunk_paths", C.c_uint32), ("tail_tasks", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("chunk_paths", C.c_uint32), ("tail_tasks", C.c_uint32), ("blocks_per_sm", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 MODE_AUTO, MODE_PER_LANE, MODE_PER_WARP, MODE_BINNED = 0, 1, 2, 3

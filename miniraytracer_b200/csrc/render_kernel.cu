@@ -692,6 +692,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, (int) threads, smem);
         if (e != cudaSuccess) { set_error(std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e)); return MRT_E_CUDA; }
         if (blocks_per_sm < 1) { set_error("render kernel does not fit on an SM (traversal stack too deep)"); return MRT_E_CUDA; }
+        if (tn.blocks_per_sm && (int) tn.blocks_per_sm < blocks_per_sm) blocks_per_sm = (int) tn.blocks_per_sm;
         resident_warps = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm * warps_per_block;
         return MRT_OK;
     };

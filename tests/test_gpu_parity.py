@@ -287,7 +287,8 @@ def test_binned_result_does_not_depend_on_the_schedule():
     """Mode B sums the finished samples of a pixel in item order from its staging array, so the accumulator is
     bit-identical whatever the bins, the chunk size or the launch bounds (i.e. whichever lane ran which path)."""
     ref = None
-    for tuning in (dict(bins=1), dict(bins=2), dict(bins=3), dict(bins=2, chunk_pixels=3), dict(bins=2, min_blocks=8)):
+    for tuning in (dict(bins=1), dict(bins=2), dict(bins=3), dict(bins=2, chunk_pixels=3), dict(bins=2, min_blocks=8),
+                   dict(chunk_paths=512), dict(chunk_paths=1024, tail_tasks=8)):
         acc, st = _gpu_render(6, 128, 72, 64, tuning=tuning)
         assert st["mode"] == api.MODE_BINNED
         if ref is None: ref = acc
