@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_per_lane(const Rend
 //   * else (chunk drained) pops what is left,
 // runs ONE segment for them (path_step, single call site), writes finished samples to the chunk's staging array
 // (global memory, one float4 per item) and parks the survivors again.  At the end of the chunk every pixel's
-// samples are summed from the staging array in item order, so the result does not depend on the schedule at all;
+// samples are summed from the staging array in an order fixed by the launch's samples per pixel alone (SEQ: one after
+// the other; else lane-strided + shuffle tree), so the result does not depend on the schedule at all;
 // per-path arithmetic is untouched (same RNG stream, same operations).
 // A live path carries no radiance (only lights and the sky emit, and both end the path), so L is not parked.
 __device__ __forceinline__ void park_path(uint32_t *pool, uint32_t slot, const Path &p, const Rng &rng, uint32_t item) {
@@ -370,7 +371,6 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
         atomicMax(&a.counters[8], ~t_entry);
         atomicAdd(&a.counters[10], 0ull - t_entry);
     }
-
 
     for (;;) {
         uint32_t task = 0;
