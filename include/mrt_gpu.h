@@ -123,7 +123,9 @@ typedef struct MrtTuning {
 #define MRT_MODE_AUTO 0u
 #define MRT_MODE_PER_LANE 1u /* a lane owns a pixel and adds its samples in the reference's order (main.cpp:154-166) */
 #define MRT_MODE_PER_WARP 2u /* a warp owns a chunk of pixels; lanes keep their paths */
-#define MRT_MODE_BINNED 3u   /* a warp owns a chunk; paths are parked and regrouped between segments (default) */
+#define MRT_MODE_BINNED 3u   /* a warp owns a chunk; paths are parked and regrouped between segments (default).  A pixel's samples are
+                                summed in an order fixed by the launch's samples per pixel: <= 128 -> one after the other (the reference's
+                                order), more -> lane-strided partial sums + a fixed tree; never dependent on the schedule */
 int mrt_gpu_set_tuning(MrtScene *s, const MrtTuning *t /* NULL = defaults */);
 /* Launch on this CUDA stream (a cudaStream_t passed as void*; NULL = default stream). */
 int mrt_gpu_set_stream(MrtScene *s, void *cuda_stream);
