@@ -697,7 +697,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         return MRT_OK;
     };
     if (binned) {
-        // chunk = warp task: ~4096 paths whatever the samples per pixel (the sums live in a staging array in global
+        // chunk = warp task: 2048 ... 8192 paths whatever the samples per pixel (the sums live in a staging array in global
         // memory, not in shared memory), but at least 10 / 32 tasks per resident warp on small frames, at least 256 paths
         int rc = occupancy(0);
         if (rc) return rc;
@@ -707,10 +707,11 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         // pixels: measured 176 -> 249 ms on a 960x540x256 frame of scene 7 with 10), >= 64 for the per-lane tree scenes (15-fold:
         // 178 -> 156 ms on that frame, warps at work 78 % -> 95 % of the launch, although fewer lanes hold a path: 93 % -> 88 %)
         uint64_t target = total / ((uint64_t) resident_warps * (s->has_trees ? (coop ? 32u : 64u) : 10u));
-        // big chunks: 4096 paths; 2048 for the per-lane tree scenes, whose chunks differ 15-fold in cost (pixels on the glass / fog of
+        // big chunks: 4096 paths for the triangle meshes; 2048 for the per-lane tree scenes, whose chunks differ 15-fold in cost (pixels on the glass / fog of
         // scene 7): a heavy 4096-path chunk handed out late outlasts the whole guided tail (warps at work 94 % -> 99.9 % of a
         // 512-sample 1080p slice, 1111 -> 1065 ms; the triangle meshes lose 0.7 % with 2048; profiles/r2_notes.md)
-        const uint64_t cap = tn.chunk_paths ? tn.chunk_paths : ((s->has_trees && !coop) ? 2048u : 4096u);
+        // list scenes: as big as the staging array allows (8192: lanes with a path 98.2 -> 99.1 %, C2 313.2 -> 311.5 ms, C3 331.8 -> 329.0)
+        const uint64_t cap = tn.chunk_paths ? tn.chunk_paths : (s->has_trees ? (coop ? 4096u : 2048u) : kMaxStageItems);
         if (target > cap) target = cap;
         if (target < 256u) target = 256u;
         K = (uint32_t) (target / ns);
