@@ -20,7 +20,7 @@ EXE = os.path.join(ROOT, "miniraytracer_b200", "mrt_b200")
 HOST_SRCS = ["scene_graph.cpp", "scenes.cpp", "obj_loader.cpp", "scene_dump.cpp", "flatten.cpp", "host_api.cpp"]
 CUDA_SRCS = ["render_kernel.cu", "render_variant_cornell.cu", "render_variant_cornell_vol.cu", "render_variant_lists.cu", "render_variant_lists_vol.cu",
              "render_variant_trees.cu", "render_variant_trees_tex.cu", "render_variant_all.cu", "render_variant_full.cu"]
-HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", "coop_tree.cuh", "render_kernels.cuh", "render_variants.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
+HEADERS = ["scene_graph.h", "trace_core.h", "mrt_libm.h", "gpu_internal.h", "coop_tree.cuh", "render_kernels.cuh", "render_variants.h", "schedule.h", os.path.join(INC, "mrt_types.h"), os.path.join(INC, "mrt_gpu.h")]
 
 EXTRA = os.environ.get("MRT_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

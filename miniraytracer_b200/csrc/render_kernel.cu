@@ -18,6 +18,7 @@
 #include "scene_graph.h"
 #include "render_kernels.cuh"
 #include "render_variants.h"
+#include "schedule.h"
 
 namespace mrt {
 
@@ -677,6 +678,7 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     // choose the task size so that every resident warp gets several tasks (load balance) while the idle
     // tail of a task stays small against its body
     uint32_t K = 1;
+    BinnedPlan plan = {};
     size_t smem = 0;
     int blocks_per_sm = 0;
     uint32_t resident_warps = 0;
@@ -701,24 +703,8 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
         // memory, not in shared memory), but at least 10 / 32 tasks per resident warp on small frames, at least 256 paths
         int rc = occupancy(0);
         if (rc) return rc;
-        const uint64_t total = (uint64_t) n_pixels * ns;
-        // >= 10 big tasks per resident warp for list scenes (chunks cost about the same; the end of the launch is balanced by the
-        // small last chunks, below), >= 32 for scenes with trees, whose chunks differ several-fold in cost (mesh vs background
-        // pixels: measured 176 -> 249 ms on a 960x540x256 frame of scene 7 with 10), >= 64 for the per-lane tree scenes (15-fold:
-        // 178 -> 156 ms on that frame, warps at work 78 % -> 95 % of the launch, although fewer lanes hold a path: 93 % -> 88 %)
-        uint64_t target = total / ((uint64_t) resident_warps * (s->has_trees ? (coop ? 32u : 64u) : 10u));
-        // big chunks: 4096 paths for the triangle meshes; 2048 for the per-lane tree scenes, whose chunks differ 15-fold in cost (pixels on the glass / fog of
-        // scene 7): a heavy 4096-path chunk handed out late outlasts the whole guided tail (warps at work 94 % -> 99.9 % of a
-        // 512-sample 1080p slice, 1111 -> 1065 ms; the triangle meshes lose 0.7 % with 2048; profiles/r2_notes.md)
-        // list scenes: as big as the staging array allows (8192: lanes with a path 98.2 -> 99.1 %, C2 313.2 -> 311.5 ms, C3 331.8 -> 329.0)
-        const uint64_t cap = tn.chunk_paths ? tn.chunk_paths : (s->has_trees ? (coop ? 4096u : 2048u) : kMaxStageItems);
-        if (target > cap) target = cap;
-        if (target < 256u) target = 256u;
-        K = (uint32_t) (target / ns);
-        if (tn.chunk_pixels) K = tn.chunk_pixels;
-        if (K < 1u) K = 1u;
-        if ((uint64_t) K * ns > kMaxStageItems) K = kMaxStageItems / ns;
-        if (K > n_pixels) K = n_pixels;
+        plan = plan_binned_schedule(n_pixels, ns, resident_warps, s->has_trees != 0u, coop, tn, kMaxStageItems);   // schedule.h
+        K = plan.K;
     } else if (mode_w) {
         // chunk = pixels per warp task: small, so that the queue holds many short tasks (a task of 8 pixels x
         // 4096 samples keeps a warp busy for ~0.1 s and the warps that finish early idle at the end of the
@@ -747,21 +733,9 @@ extern "C" int mrt_gpu_render_async(MrtScene *s, const MrtRenderParams *p) {
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
     if (binned) {
-        // Guided self-scheduling: big chunks first, the last stretch of the frame -- about two big chunks per resident warp --
-        // in chunks of a quarter and then a sixteenth of that size, so that at the end of the launch a warp waits for a
-        // small chunk, not a big one (with 18 big chunks per warp, the 1/8 slice of an 8-GPU run, the idle end was 3-5 %
-        // of the launch; profiles/r2_notes.md).  MrtTuning.chunk_pixels = uniform chunks of that size.
-        uint32_t k1 = K / 4u ? K / 4u : 1u, k2 = K / 16u ? K / 16u : 1u;
-        uint64_t tail = tn.chunk_pixels ? 0u : (uint64_t) (tn.tail_tasks ? tn.tail_tasks : 2u) * resident_warps * K;     // pixels handed out in small chunks
-        if (tail > n_pixels / 4u) tail = n_pixels / 4u;
-        if (k1 == K) tail = 0;
-        const uint32_t p1 = n_pixels - (uint32_t) tail;                                 // run 0: [0, p1) in chunks of K
-        const uint32_t p2 = (k2 == k1) ? n_pixels : p1 + (uint32_t) (tail * 2u / 3u);   // run 1: [p1, p2) in chunks of k1; run 2: the rest
-        const uint32_t t1 = (p1 + K - 1u) / K, t2 = t1 + (p2 - p1 + k1 - 1u) / k1;
-        a.sched_task0[0] = 0; a.sched_task0[1] = t1; a.sched_task0[2] = t2;
-        a.sched_pix0[0] = 0; a.sched_pix0[1] = p1; a.sched_pix0[2] = p2; a.sched_pix0[3] = n_pixels;
-        a.sched_k[0] = K; a.sched_k[1] = k1; a.sched_k[2] = k2;
-        a.n_tasks = t2 + (n_pixels - p2 + k2 - 1u) / k2;
+        for (int r = 0; r < 3; r++) { a.sched_task0[r] = plan.task0[r]; a.sched_pix0[r] = plan.pix0[r]; a.sched_k[r] = plan.k[r]; }
+        a.sched_pix0[3] = plan.pix0[3];
+        a.n_tasks = plan.n_tasks;
     }
     uint32_t grid = (uint32_t) s->sm_count * (uint32_t) blocks_per_sm;
     const uint32_t blocks_needed = (a.n_tasks + warps_per_block - 1) / warps_per_block;

@@ -11,6 +11,7 @@
 
 #include "scene_graph.h"
 #include "render_kernels.cuh"
+#include "schedule.h"
 
 using namespace mrt;
 
@@ -89,7 +90,19 @@ int main(int argc, char **argv) {
     if (g_mode == 'P') K = chunk ? ((chunk + 31u) & ~31u) : 32u;
     a.pixels_per_task = K;
     a.n_tasks = (n_pixels + K - 1) / K;
-    {   // guided schedule of the ticket queue (see mrt_gpu_render_async): -tail P = the last P pixels in chunks of K/4 and K/16
+    const uint32_t plan_warps = strtoul(argval(argc, argv, "-plan", "0"), 0, 0);
+    if (plan_warps && g_mode == 'B') {
+        // -plan W: the shipped planner (schedule.h, as called by mrt_gpu_render_async) for W resident warps
+        MrtTuning tn; memset(&tn, 0, sizeof(tn));
+        tn.chunk_pixels = chunk;
+        tn.chunk_paths = strtoul(argval(argc, argv, "-chunkpaths", "0"), 0, 0);
+        const BinnedPlan pl = plan_binned_schedule(n_pixels, ns, plan_warps, d.n_node2 != 0, g_coop, tn, kMaxStageItems);
+        K = pl.K;
+        a.pixels_per_task = K;
+        for (int r = 0; r < 3; r++) { a.sched_task0[r] = pl.task0[r]; a.sched_pix0[r] = pl.pix0[r]; a.sched_k[r] = pl.k[r]; }
+        a.sched_pix0[3] = pl.pix0[3];
+        a.n_tasks = pl.n_tasks;
+    } else {   // ad hoc: -tail P = the last P pixels in chunks of K/4 and K/16
         uint32_t tail = strtoul(argval(argc, argv, "-tail", "0"), 0, 0);
         if (tail > n_pixels) tail = n_pixels;
         const uint32_t k1 = K / 4u ? K / 4u : 1u, k2 = K / 16u ? K / 16u : 1u;

@@ -56,6 +56,16 @@ def test_mode_b_result_is_schedule_independent(emul_kernel_bin):
 
 
 @needs_ref
+def test_mode_b_with_the_shipped_planner(emul_kernel_bin):
+    """-plan W: the ticket queue laid out by schedule.h (the planner mrt_gpu_render_async calls) for W resident warps -- big chunks,
+    then quarter and sixteenth chunks -- gives the same accumulator as one-pixel chunks."""
+    base, _ = oracle_util.emul_binned(emul_kernel_bin, 6, 40, 22, 16, bins=2, chunk=1)
+    for warps, extra in ((1, ()), (2, ("-chunkpaths", "512")), (4, ())):
+        acc, meta = oracle_util.emul_binned(emul_kernel_bin, 6, 40, 22, 16, bins=2, extra=("-plan", str(warps)) + extra)
+        np.testing.assert_array_equal(acc, base)
+
+
+@needs_ref
 def test_mode_b_sample_slice(emul_kernel_bin):
     ref, rmeta = oracle_util.ref_render(5, 20, 11, 49, s0=10, s1=37)
     acc, meta = oracle_util.emul_binned(emul_kernel_bin, 5, 20, 11, 49, s0=10, s1=37)
