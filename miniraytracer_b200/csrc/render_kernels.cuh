@@ -365,7 +365,12 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
     float4 *stage = a.stage + ((size_t) blockIdx.x * kWarpsPerBlock + warp) * (size_t) a.stage_items;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t ns = a.s_end - a.s_begin;
-    uint32_t rays = 0, iters = 0;   // of the current chunk (flushed to the 64-bit counters at its end: two registers in the segment loop, not six)
+    // Statistics.  The 80-register kernels of the list scenes count rays and iterations per CHUNK, warp-uniform, in two 32-bit
+    // registers flushed at the chunk end (C3 329 -> 317 ms: the segment loop is at the edge of its register budget); the 96-register
+    // tree kernels keep three 64-bit per-lane counters for the whole launch (the per-chunk form cost them 1 %; profiles/r2_notes.md).
+    constexpr bool kChunkCounters = (FEAT & MRT_FEAT_TREES) == 0;
+    uint32_t rays = 0, iters = 0;                          // kChunkCounters
+    unsigned long long rays64 = 0, nonfinite64 = 0, iters64 = 0;   // !kChunkCounters
     if (lane == 0) {   // when the warps were at work (MrtRenderStats.warp_time_sum_ns ...): nothing kept in a register across the launch
         const unsigned long long t_entry = warp_clock_ns();
         atomicMax(&a.counters[8], ~t_entry);
@@ -441,15 +446,16 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
                 }
                 if (active) unpark_path(pool, slot, p, rng, k);
             }
-            iters++;
             bool cont = false;
-            rays += n;   // lanes with a path in this step (warp-uniform)
+            if constexpr (kChunkCounters) { iters++; rays += n; }   // n = lanes with a path in this step (warp-uniform)
+            else { iters64++; if (active) rays64++; }
             if constexpr (COOP) cont = path_step_coop<FEAT>(a, p, rng, st, active, ca, cstats);
             else if (active) cont = path_step<FEAT>(a, p, rng, st);
             if (active && !cont) {
                 const bool fin = path_sample_finite(p);
                 __stcs(stage + k, fin ? make_float4(p.L.x, p.L.y, p.L.z, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f));
-                if (!fin) atomicAdd(&a.counters[2], 1ull);   // rare
+                if constexpr (kChunkCounters) { if (!fin) atomicAdd(&a.counters[2], 1ull); }   // rare
+                else if (!fin) nonfinite64++;
             }
             // slots: finished paths return theirs, new survivors take one (never both in one iteration)
             const uint32_t m_free = __ballot_sync(0xFFFFFFFFu, active && !cont && slot != 0xFFu);
@@ -536,15 +542,30 @@ __global__ void __launch_bounds__(kBlock, MINB) render_pixel_binned(const Render
                 }
             }
         }
-        if (lane == 0) {
-            atomicAdd(&a.counters[3], warp_clock_ns() - t_sum0);   // MrtRenderStats.stage_sum_ns
-            atomicAdd(&a.counters[0], (unsigned long long) rays);
-            atomicAdd(&a.counters[1], (unsigned long long) iters);
+        if constexpr (kChunkCounters) {
+            if (lane == 0) {
+                atomicAdd(&a.counters[3], warp_clock_ns() - t_sum0);   // MrtRenderStats.stage_sum_ns
+                atomicAdd(&a.counters[0], (unsigned long long) rays);
+                atomicAdd(&a.counters[1], (unsigned long long) iters);
+            }
+            rays = 0; iters = 0;
+        } else {
+            if (lane == 0) atomicAdd(&a.counters[3], warp_clock_ns() - t_sum0);   // MrtRenderStats.stage_sum_ns
         }
-        rays = 0; iters = 0;
         __syncwarp();
     }
+    if constexpr (!kChunkCounters) {
+        for (int o = 16; o > 0; o >>= 1) {
+            rays64 += __shfl_xor_sync(0xFFFFFFFFu, rays64, o);
+            nonfinite64 += __shfl_xor_sync(0xFFFFFFFFu, nonfinite64, o);
+        }
+    }
     if (lane == 0) {
+        if constexpr (!kChunkCounters) {
+            atomicAdd(&a.counters[0], rays64);
+            atomicAdd(&a.counters[1], iters64);
+            atomicAdd(&a.counters[2], nonfinite64);
+        }
         if (COOP) {
             atomicAdd(&a.counters[4], cs_node_steps); atomicAdd(&a.counters[5], cs_node_items);
             atomicAdd(&a.counters[6], cs_leaf_steps); atomicAdd(&a.counters[7], cs_leaf_items);

@@ -32,12 +32,18 @@ static RenderArgs g_args;
 static char g_mode = 'B';
 static bool g_coop = false;
 static bool g_seq = false;   // launches with <= kStageBlock samples per pixel use the SEQ instantiation (render_kernel.cu)
+static bool g_trees = true;   // scenes without BVH trees run a mask without MRT_FEAT_TREES, like the product's specialised variants
+template <uint32_t FEAT>
+static void entry_b() {
+    if (g_seq) { if (g_coop) render_pixel_binned<FEAT, 6, true, true>(g_args); else render_pixel_binned<FEAT, 6, false, true>(g_args); }
+    else if (g_coop) render_pixel_binned<FEAT, 6, true, false>(g_args);
+    else render_pixel_binned<FEAT, 6, false, false>(g_args);
+}
 static void entry(void *) {
     if (g_mode == 'W') render_pixel_per_warp<MRT_FEAT_ALL, 6>(g_args);
     else if (g_mode == 'P') render_pixel_per_lane<MRT_FEAT_ALL, 6>(g_args);
-    else if (g_seq) { if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true, true>(g_args); else render_pixel_binned<MRT_FEAT_ALL, 6, false, true>(g_args); }
-    else if (g_coop) render_pixel_binned<MRT_FEAT_ALL, 6, true, false>(g_args);
-    else render_pixel_binned<MRT_FEAT_ALL, 6, false, false>(g_args);
+    else if (g_trees) entry_b<MRT_FEAT_ALL>();
+    else entry_b<(MRT_FEAT_ALL & ~(MRT_FEAT_TREES | MRT_FEAT_TRIS))>();
 }
 
 int main(int argc, char **argv) {
@@ -77,6 +83,7 @@ int main(int argc, char **argv) {
     a.crop_x0 = x0; a.crop_y0 = y0; a.crop_w = CW; a.n_pixels = n_pixels;
     a.width = W; a.height = H; a.sqrt_n = sq; a.s_begin = s0; a.s_end = s1; a.max_bounces = depth; a.seed = seed;
     g_seq = (s1 - s0) <= kStageBlock;
+    g_trees = d.n_node2 != 0;
     a.accumulate = 0;
     a.stack_words = d.stack_words ? d.stack_words : 64;
     if (g_coop) {
